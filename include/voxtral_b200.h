@@ -356,9 +356,31 @@ typedef struct {
     double last_encoder_kernel_ms;       /* device time of the last encoder+adapter pass */
     int    last_encoder_positions;
     double last_mel_kernel_ms;
+    double total_decode_kernel_ms;       /* cumulative device time inside decode steps (CUDA events) */
+    long long total_decode_steps;
+    double total_encoder_ms;             /* cumulative host-observed time of encoder+adapter passes */
+    long long total_encoder_positions;
 } vox_cuda_info_t;
 int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out);
 const char *vox_cuda_version(void);
+/* Forget both KV caches (decoder ring positions and encoder tail), like a freshly loaded ctx. */
+void vox_cuda_reset_caches(vox_ctx_t *ctx);
+
+/* Same as vox_stream_feed but the PCM already lives in HBM (d_samples is a DEVICE pointer on the
+ * ctx's device): the path a GPU-resident audio front end would use, and what bench.py times for the
+ * "inputs resident in HBM" figure. */
+int vox_cuda_stream_feed_device(vox_stream_t *s, const float *d_samples, int n_samples);
+
+/* Minimal device-memory helpers so a host program can stage buffers for the calls above
+ * without linking the CUDA runtime itself. */
+void *vox_cuda_malloc(vox_ctx_t *ctx, size_t bytes);
+void  vox_cuda_free(vox_ctx_t *ctx, void *d_ptr);
+int   vox_cuda_memcpy_h2d(vox_ctx_t *ctx, void *d_dst, const void *h_src, size_t bytes);
+int   vox_cuda_memcpy_d2h(vox_ctx_t *ctx, void *h_dst, const void *d_src, size_t bytes);
+
+/* Device-timeline stopwatch on the ctx's stream (CUDA events): start, run any API calls, stop. */
+void   vox_cuda_timer_start(vox_ctx_t *ctx);
+double vox_cuda_timer_stop_ms(vox_ctx_t *ctx);
 
 /* Copy the device stream state a test wants to inspect back to the host. */
 int vox_cuda_stream_token_ids(vox_stream_t *s, int *out, int max);   /* all ids generated so far */

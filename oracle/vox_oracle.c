@@ -1,0 +1,1 @@
+#include "vox_oracle.h"

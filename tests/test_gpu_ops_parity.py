@@ -1,0 +1,206 @@
+"""Per-op parity: every function of the kernel dispatch surface (reference voxtral_kernels.h) called
+through the C ABI of libvoxtral_b200.so on host buffers, against the SAME function of the unmodified
+reference (oracle/_ref/libvoxref.so) on the same seeded inputs.
+
+Tolerances: f32 elementwise ops -> a few ulp; dot-product ops (GEMV/GEMM/conv/attention/norm) -> relative
+1e-5 of the output scale (the reference itself is -ffast-math + OpenBLAS, i.e. its summation order is
+not canonical).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+fp = C.POINTER(C.c_float)
+u16p = C.POINTER(C.c_uint16)
+
+
+def P(a):
+    return a.ctypes.data_as(fp)
+
+
+def bf16_weights(rng, n, k, scale):
+    w = (rng.uniform(-1, 1, size=(n, k)) * scale).astype(np.float32)
+    u = w.view(np.uint32)
+    u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)          # RNE to bf16
+    return np.ascontiguousarray(u)
+
+
+def close(a, b, rtol):
+    scale = max(float(np.abs(b).max()), 1e-6)
+    err = float(np.abs(a - b).max())
+    assert err <= rtol * scale, f"max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.2e} > {rtol})"
+
+
+@pytest.mark.parametrize("op", ["silu", "gelu"])
+def test_activations(vb, ref, op):
+    rng = np.random.default_rng(1)
+    x = rng.normal(0, 3, size=5000).astype(np.float32)
+    a, b = x.copy(), x.copy()
+    getattr(vb.lib(), "vox_" + op)(P(a), a.size)
+    getattr(ref.L, "vox_" + op)(P(b), b.size)
+    close(a, b, 2e-6)
+
+
+def test_elementwise(vb, ref):
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=4097).astype(np.float32)
+    y = rng.normal(size=4097).astype(np.float32)
+    for name, args in (("vox_add_inplace", (P(y),)), ("vox_mul_inplace", (P(y),))):
+        a, b = x.copy(), x.copy()
+        getattr(vb.lib(), name)(P(a), *args, a.size)
+        getattr(ref.L, name)(P(b), *args, b.size)
+        assert np.array_equal(a, b), name
+    a, b = x.copy(), x.copy()
+    vb.lib().vox_axpy(P(a), 0.37, P(y), a.size)
+    ref.L.vox_axpy(P(b), 0.37, P(y), b.size)
+    close(a, b, 1e-6)
+    a, b = x.copy(), x.copy()
+    vb.lib().vox_scale(P(a), 1.7, a.size)
+    ref.L.vox_scale(P(b), 1.7, b.size)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("rows,hidden", [(1, 3072), (7, 1280), (3, 96)])
+def test_rms_norm(vb, ref, rows, hidden):
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(rows, hidden)).astype(np.float32)
+    w = rng.uniform(0.9, 1.1, size=hidden).astype(np.float32)
+    a, b = np.empty_like(x), np.empty_like(x)
+    vb.lib().vox_rms_norm(P(a), P(x), P(w), rows, hidden, 1e-5)
+    ref.L.vox_rms_norm(P(b), P(x), P(w), rows, hidden, 1e-5)
+    close(a, b, 2e-6)
+
+
+# (M, K, N): decode GEMV shapes, prefill/encoder GEMM shapes, ragged sizes
+@pytest.mark.parametrize("M,K,N,bias", [
+    (1, 3072, 4096, False), (1, 3072, 1024, False), (1, 4096, 3072, False), (1, 9216, 3072, False),
+    (1, 3072, 9216, False), (1, 1280, 2048, True), (1, 5120, 1280, True),
+    (38, 3072, 1024, False), (5, 1280, 2048, True), (130, 2048, 1280, True), (3, 384, 70, True),
+])
+def test_linear_bf16(vb, ref, M, K, N, bias):
+    rng = np.random.default_rng(4 + M + K + N)
+    x = rng.normal(size=(M, K)).astype(np.float32)
+    W = bf16_weights(rng, N, K, np.sqrt(3.0 / K))
+    b = rng.normal(size=N).astype(np.float32) * 0.1 if bias else None
+    ya, yb = np.empty((M, N), np.float32), np.empty((M, N), np.float32)
+    bp = P(b) if bias else None
+    vb.lib().vox_linear_bf16(P(ya), P(x), W.ctypes.data_as(u16p), bp, M, K, N)
+    ref.L.vox_linear_bf16(P(yb), P(x), W.ctypes.data_as(u16p), bp, M, K, N)
+    close(ya, yb, 1e-5)
+
+
+def test_linear_f32_and_matmul(vb, ref):
+    rng = np.random.default_rng(5)
+    M, K, N = 9, 200, 33
+    x = rng.normal(size=(M, K)).astype(np.float32)
+    W = rng.normal(size=(N, K)).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    ya, yb = np.empty((M, N), np.float32), np.empty((M, N), np.float32)
+    vb.lib().vox_linear(P(ya), P(x), P(W), P(b), M, K, N)
+    ref.L.vox_linear(P(yb), P(x), P(W), P(b), M, K, N)
+    close(ya, yb, 1e-5)
+    B = rng.normal(size=(K, N)).astype(np.float32)
+    vb.lib().vox_matmul(P(ya), P(x), P(B), M, K, N)
+    ref.L.vox_matmul(P(yb), P(x), P(B), M, K, N)
+    close(ya, yb, 1e-5)
+
+
+def test_softmax(vb, ref):
+    rng = np.random.default_rng(6)
+    x = (rng.normal(size=(3, 1000)) * 4).astype(np.float32)
+    a, b = x.copy(), x.copy()
+    vb.lib().vox_softmax(P(a), 3, 1000)
+    ref.L.vox_softmax(P(b), 3, 1000)
+    close(a, b, 1e-5)
+
+
+@pytest.mark.parametrize("seq_q,seq_k,H,Hkv,hd,win,qoff", [
+    (1, 300, 32, 8, 128, 8192, 299),        # decode step, GQA
+    (38, 38, 32, 8, 128, 8192, 0),          # prefill
+    (20, 820, 32, 32, 64, 750, 800),        # encoder chunk against a full window (mask on both sides)
+    (9, 9, 4, 2, 32, 3, 0),                 # tiny window
+])
+def test_causal_attention(vb, ref, seq_q, seq_k, H, Hkv, hd, win, qoff):
+    rng = np.random.default_rng(7 + seq_q)
+    Q = rng.normal(size=(seq_q, H * hd)).astype(np.float32)
+    K = rng.normal(size=(seq_k, Hkv * hd)).astype(np.float32)
+    V = rng.normal(size=(seq_k, Hkv * hd)).astype(np.float32)
+    a, b = np.empty_like(Q), np.empty_like(Q)
+    scale = 1.0 / np.sqrt(hd)
+    vb.lib().vox_causal_attention(P(a), P(Q), P(K), P(V), seq_q, seq_k, H, Hkv, hd, scale, win, qoff)
+    ref.L.vox_causal_attention(P(b), P(Q), P(K), P(V), seq_q, seq_k, H, Hkv, hd, scale, win, qoff)
+    close(a, b, 2e-5)
+
+
+@pytest.mark.parametrize("hd,heads,pos0", [(128, 8, 0), (64, 32, 180000), (128, 32, 9000)])
+def test_rope(vb, ref, hd, heads, pos0):
+    rng = np.random.default_rng(8)
+    seq = 5
+    pos = (np.arange(seq) + pos0).astype(np.int32)
+    fa, fb = np.empty((seq, hd), np.float32), np.empty((seq, hd), np.float32)
+    vb.lib().vox_compute_rope_freqs(P(fa), pos.ctypes.data_as(C.POINTER(C.c_int)), seq, hd, 1e6)
+    ref.L.vox_compute_rope_freqs(P(fb), pos.ctypes.data_as(C.POINTER(C.c_int)), seq, hd, 1e6)
+    close(fa, fb, 1e-6)
+    x = rng.normal(size=(seq, heads * hd)).astype(np.float32)
+    a, b = x.copy(), x.copy()
+    vb.lib().vox_apply_rope(P(a), P(fb), seq, heads, hd)
+    ref.L.vox_apply_rope(P(b), P(fb), seq, heads, hd)
+    close(a, b, 2e-6)
+
+
+@pytest.mark.parametrize("cin,cout,L,stride", [(128, 64, 50, 1), (64, 48, 50, 2), (64, 48, 51, 2)])
+def test_causal_conv1d(vb, ref, cin, cout, L, stride):
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(cin, L)).astype(np.float32)
+    w = (rng.normal(size=(cout, cin, 3)) * 0.05).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    out_len = L if stride == 1 else (L + 1) // 2
+    ya, yb = np.zeros((cout, out_len), np.float32), np.zeros((cout, out_len), np.float32)
+    vb.lib().vox_causal_conv1d(P(ya), P(x), P(w), P(b), cin, cout, L, 3, stride)
+    ref.L.vox_causal_conv1d(P(yb), P(x), P(w), P(b), cin, cout, L, 3, stride)
+    close(ya, yb, 1e-5)
+    # symmetric-padding variant
+    out_len = (L + 2 - 3) // stride + 1
+    ya, yb = np.zeros((cout, out_len), np.float32), np.zeros((cout, out_len), np.float32)
+    vb.lib().vox_conv1d(P(ya), P(x), P(w), P(b), cin, cout, L, 3, stride, 1)
+    ref.L.vox_conv1d(P(yb), P(x), P(w), P(b), cin, cout, L, 3, stride, 1)
+    close(ya, yb, 1e-5)
+
+
+def _mel_stream(L, pcm, chunks, free):
+    ctx = L.vox_mel_ctx_init(32 * 1280)
+    off = 0
+    for c in chunks:
+        seg = np.ascontiguousarray(pcm[off:off + c]); off += c
+        if seg.size:
+            L.vox_mel_feed(ctx, P(seg), seg.size)
+    z = np.zeros(17 * 1280, np.float32)
+    L.vox_mel_feed(ctx, P(z), z.size)
+    L.vox_mel_finish(ctx, 0)
+    n = C.c_int()
+    p = L.vox_mel_data(ctx, C.byref(n))
+    out = np.ctypeslib.as_array(p, shape=(n.value, 128)).copy()
+    L.vox_mel_free(ctx)
+    return out
+
+
+def test_mel_batch_and_stream(vb, ref):
+    from conftest import read_wav_f32, synth_wav
+    pcm = read_wav_f32(synth_wav(2))
+    n1, n2 = C.c_int(), C.c_int()
+    pa = vb.lib().vox_mel_spectrogram(P(pcm), pcm.size, C.byref(n1))
+    pb = ref.L.vox_mel_spectrogram(P(pcm), pcm.size, C.byref(n2))
+    assert n1.value == n2.value == 200
+    a = np.ctypeslib.as_array(pa, shape=(n1.value, 128)).copy()
+    b = np.ctypeslib.as_array(pb, shape=(n2.value, 128)).copy()
+    # log-mel values are O(1); 1e-4 abs covers log10 of tiny, clamped bins computed in another order
+    assert np.abs(a - b).max() < 2e-4, np.abs(a - b).max()
+    # streaming: same frames regardless of how the audio is chunked; equals the reference stream mel
+    sa = _mel_stream(vb.lib(), pcm, [pcm.size], None)
+    sb = _mel_stream(ref.L, pcm, [pcm.size], None)
+    sc = _mel_stream(vb.lib(), pcm, [1000, 160, 1, 7777, pcm.size], None)
+    assert sa.shape == sb.shape == sc.shape
+    assert np.abs(sa - sb).max() < 2e-4
+    assert np.array_equal(sa, sc)

@@ -1,0 +1,82 @@
+"""Whole-pipeline parity through the streaming C API: PCM in -> greedy token ids out, against golden
+traces of the UNMODIFIED reference (tests/golden/*.npz, produced by oracle/ref_trace + tools/make_goldens.py
+on the same seeded checkpoint and PCM), plus chunking-invariance properties that need no oracle.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, read_wav_f32, synth_wav
+
+pytestmark = pytest.mark.gpu
+
+
+def run_stream(engine, pcm, chunk=None, interval=None):
+    s = engine.stream()
+    if interval is not None:
+        s.set_interval(interval)
+    if chunk is None:
+        s.feed(pcm)
+    else:
+        for off in range(0, pcm.size, chunk):
+            s.feed(pcm[off:off + chunk])
+    s.finish()
+    text = b"".join(s.get())
+    ids = s.token_ids().copy()
+    counts = s.counts()
+    s.close()
+    return ids, text, counts
+
+
+def margin_ok_positions(g, thr=2e-3):
+    return (g["top_val"][:, 0] - g["top_val"][:, 1]) > thr
+
+
+def check_against(g, ids, text):
+    ref_ids = g["tokens"]
+    assert len(ids) == len(ref_ids), (len(ids), len(ref_ids))
+    # greedy equality; a mismatch is only tolerated at a step where the reference's own top-1/top-2
+    # margin is below 2e-3 (and then nothing after it is comparable)
+    ok = margin_ok_positions(g)
+    for i, (a, b) in enumerate(zip(ids, ref_ids)):
+        if a != b:
+            assert not ok[i], f"token mismatch at step {i}: {a} vs {b} (reference margin {g['top_val'][i,0]-g['top_val'][i,1]:.3e})"
+            pytest.skip(f"near-tie flip at step {i}; later steps are not comparable")
+    assert text == g["text"].tobytes()
+
+
+def test_oneshot_tokens_match_reference(engine):
+    g = golden("synth_s2_oneshot")
+    pcm = read_wav_f32(synth_wav(2))
+    assert pcm.size == int(g["samples"])
+    ids, text, counts = run_stream(engine, pcm)
+    print("ids", ids.tolist())
+    assert counts["adapter_tokens"] == 74 and counts["mel_frames"] == 592
+    check_against(g, ids, text)
+
+
+def test_chunked_1s_tokens_match_reference(engine):
+    g = golden("synth_s2_chunk1s")
+    pcm = read_wav_f32(synth_wav(2))
+    ids, text, _ = run_stream(engine, pcm, chunk=16000)
+    check_against(g, ids, text)
+
+
+def test_chunking_invariance(engine):
+    """The incremental path must not depend on how the caller slices the audio (same mel frames, same
+    conv/encoder rows up to f32 reordering) -- the tiny-interval run exercises the conv tails, the odd
+    conv0 residual, the 4x adapter residual and the encoder KV tail on every call."""
+    pcm = read_wav_f32(synth_wav(2))
+    a, ta, ca = run_stream(engine, pcm)
+    b, tb, cb = run_stream(engine, pcm, chunk=1600, interval=0.1)
+    assert ca["adapter_tokens"] == cb["adapter_tokens"] and ca["mel_frames"] == cb["mel_frames"]
+    assert a.tolist() == b.tolist()
+    assert ta == tb
+
+
+def test_feed_after_finish_and_empty(engine):
+    s = engine.stream()
+    assert s.feed(np.zeros(0, np.float32)) == -1          # n <= 0 -> -1 (voxtral.c:1237)
+    s.feed(np.zeros(1600, np.float32))
+    assert s.finish() == 0
+    assert s.finish() == -1 and s.feed(np.zeros(10, np.float32)) == -1
+    s.close()

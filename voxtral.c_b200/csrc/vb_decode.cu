@@ -1,0 +1,611 @@
+/*
+ * vb_decode.cu -- the autoregressive decoder step (HOT LOOP C of SURVEY.md section 3.1)
+ * as CUDA kernels: reference voxtral_decoder.c:586-706 (one token through 26 layers,
+ * final norm, tied-embedding logits, argmax) plus the embedding add of
+ * voxtral.c:1057-1061, all driven by device-resident state so that consecutive
+ * steps need no host round trip.
+ *
+ * Data flow per step (everything f32 except the bf16 weights, like the reference):
+ *   x = adapter[row] + tok_emb[prev]                                   k_dec_embed
+ *   26 x { RMSNorm -> [wq|wk|wv] GEMV -> RoPE -> KV ring write         k_dec_qkv
+ *          split-S GQA attention over the ring + combine               k_dec_attn_partial/_combine
+ *          wo GEMV + residual                                          k_dec_wo
+ *          RMSNorm*(1+ada) -> [w1|w3] GEMV -> SiLU(g)*u                k_dec_w13
+ *          w2 GEMV + residual }                                        k_dec_w2
+ *   RMSNorm -> 131072x3072 GEMV -> per-CTA argmax                      k_dec_logits
+ *   global argmax, state advance, token append                         k_dec_finish
+ *
+ * GEMV design (memory-bound: 6.86 GB of weights per step): every CTA owns a
+ * contiguous slab of output rows; inside the CTA each thread owns a fixed set of
+ * k-columns (8 consecutive k per 16-byte load) for ALL rows of the slab, so the
+ * activation vector lives in registers, every row is read with perfectly
+ * coalesced 128-bit streaming loads (ld.global.nc.L1::no_allocate), and R rows
+ * are in flight per thread.  Partial sums are combined with a warp transpose-
+ * reduce (R values in ~R shuffles) and one shared-memory pass.
+ */
+#include "vb_ops.cuh"
+#include <string.h>
+
+#define DT 512                       /* threads per decode CTA */
+#define DW (DT / 32)
+#define DEC_DIM   VOX_DEC_DIM
+#define DEC_HID   VOX_DEC_HIDDEN
+#define HD        VOX_DEC_HEAD_DIM
+#define NS_PER_CTA 2                 /* split-S groups per CTA in decode attention */
+
+struct DecParams {
+    const uint16_t *tok_emb;
+    const uint16_t *wqkv[VOX_DEC_LAYERS], *wo[VOX_DEC_LAYERS], *w13[VOX_DEC_LAYERS], *w2[VOX_DEC_LAYERS];
+    const float *attn_norm[VOX_DEC_LAYERS], *ffn_norm[VOX_DEC_LAYERS];
+    const float *ada;               /* [26][3072] */
+    const float *final_norm;
+    const float *inv_freq;          /* [64] */
+    float *kv_k, *kv_v;             /* [26][8192][1024] */
+    float *x, *q, *attn_out, *gate, *logits;
+    float *part_m, *part_l, *part_o;
+    unsigned long long *argmax;
+    VbDecState *st;
+    const float *const *adapter_pp; /* device slot holding the adapter base pointer */
+    int *tokens;
+    int use_embed_kernel;
+};
+
+/* ---------------------------------------------------------------- helpers */
+__device__ __forceinline__ uint4 ldg_stream16(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float dot8(const uint4 w, const float *x, float acc) {
+    acc = fmaf(vb_bf16_lo(w.x), x[0], acc); acc = fmaf(vb_bf16_hi(w.x), x[1], acc);
+    acc = fmaf(vb_bf16_lo(w.y), x[2], acc); acc = fmaf(vb_bf16_hi(w.y), x[3], acc);
+    acc = fmaf(vb_bf16_lo(w.z), x[4], acc); acc = fmaf(vb_bf16_hi(w.z), x[5], acc);
+    acc = fmaf(vb_bf16_lo(w.w), x[6], acc); acc = fmaf(vb_bf16_hi(w.w), x[7], acc);
+    return acc;
+}
+
+template <int R> struct Log2;
+template <> struct Log2<4>  { static const int v = 2; };
+template <> struct Log2<8>  { static const int v = 3; };
+template <> struct Log2<16> { static const int v = 4; };
+template <> struct Log2<32> { static const int v = 5; };
+
+/* Sum v[i] over the 32 lanes for all i<R with ~R shuffles.  Returns the total of
+ * index (lane >> (5-log2 R)); lanes sharing that index hold the same value. */
+template <int R>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[R], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = R; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) {
+            float send = upper ? v[i] : v[i + n / 2];
+            float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int o = (16 >> Log2<R>::v); o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+
+/* Thread t (< NT) loads its CPT*8 activation values: chunk c covers k = (c*NT+t)*8 .. +7 */
+template <int CPT>
+__device__ __forceinline__ void load_x_cols(float (&xr)[CPT * 8], const float *__restrict__ x, int NT) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < CPT; c++) {
+        if (t < NT) {
+            const float4 *p = reinterpret_cast<const float4 *>(x + (size_t)(c * NT + t) * 8);
+            float4 a = p[0], b = p[1];
+            xr[c * 8 + 0] = a.x; xr[c * 8 + 1] = a.y; xr[c * 8 + 2] = a.z; xr[c * 8 + 3] = a.w;
+            xr[c * 8 + 4] = b.x; xr[c * 8 + 5] = b.y; xr[c * 8 + 6] = b.z; xr[c * 8 + 7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) xr[c * 8 + j] = 0.f;
+        }
+    }
+}
+
+/* Block-wide sum (all DT threads call). */
+__device__ __forceinline__ float block_sum(float v, float *red /* [DW] */) {
+    v = vb_warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < DW; i++) t += red[i];
+    return t;
+}
+
+/* RMSNorm of the register-resident vector (voxtral_kernels.c:346-363), optional (1+ada). */
+template <int CPT>
+__device__ __forceinline__ void rmsnorm_cols(float (&xr)[CPT * 8], const float *__restrict__ w,
+                                             const float *__restrict__ ada, int NT, int hidden, float *red) {
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPT * 8; j++) ss = fmaf(xr[j], xr[j], ss);
+    float tot = block_sum(ss, red);
+    float rinv = 1.0f / sqrtf(tot / (float)hidden + VOX_DEC_NORM_EPS);
+    const int t = threadIdx.x;
+    if (t < NT) {
+#pragma unroll
+        for (int c = 0; c < CPT; c++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int k = (c * NT + t) * 8 + j;
+                float v = xr[c * 8 + j] * rinv * w[k];
+                if (ada) v *= (1.0f + ada[k]);
+                xr[c * 8 + j] = v;
+            }
+    }
+}
+
+/* y[row] = W[row,:] . x for rows [row0, row0+nrows); epi(row, value, lane, valid) runs in warp 0. */
+template <int CPT, int R, typename Epi>
+__device__ __forceinline__ void gemv_rows(const uint16_t *__restrict__ W, int K, int NT, int row0, int nrows,
+                                          const float (&xr)[CPT * 8], float (*red)[R], Epi epi) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool active = t < NT;
+    const uint16_t *wt = W + (size_t)t * 8;
+    for (int rb = 0; rb < nrows; rb += R) {
+        const int nr = min(R, nrows - rb);
+        uint4 w[R][CPT];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int c = 0; c < CPT; c++) {
+                if (active && r < nr) w[r][c] = ldg_stream16(wt + (size_t)(row0 + rb + r) * K + (size_t)c * NT * 8);
+                else w[r][c] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            float a = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPT; c++) a = dot8(w[r][c], &xr[c * 8], a);
+            acc[r] = a;
+        }
+        float tot = warp_transpose_reduce<R>(acc, lane);
+        if ((lane & ((32 >> Log2<R>::v) - 1)) == 0) red[warp][lane >> (5 - Log2<R>::v)] = tot;
+        __syncthreads();
+        if (warp == 0) {
+            float s = 0.f;
+            if (lane < R) {
+#pragma unroll
+                for (int wv = 0; wv < DW; wv++) s += red[wv][lane];
+            }
+            epi(row0 + rb + lane, s, lane, lane < nr);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void cta_rows(int total_units, int &u0, int &n) {
+    /* contiguous, balanced partition of `total_units` over the grid */
+    long long a = (long long)total_units * blockIdx.x / gridDim.x;
+    long long b = (long long)total_units * (blockIdx.x + 1) / gridDim.x;
+    u0 = (int)a; n = (int)(b - a);
+}
+
+/* ---------------------------------------------------------------- kernels */
+__global__ void __launch_bounds__(256) k_dec_embed(DecParams p) {
+    const VbDecState st = *p.st;
+    if (st.eos) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= DEC_DIM) return;
+    const float *adapter = *p.adapter_pp;
+    float a = adapter[(size_t)st.adapter_row * DEC_DIM + i];
+    float t = __uint_as_float((uint32_t)p.tok_emb[(size_t)st.token * DEC_DIM + i] << 16);
+    p.x[i] = a + t;                                      /* voxtral.c:1057-1061 */
+}
+
+__global__ void __launch_bounds__(DT, 1) k_dec_qkv(DecParams p, int layer) {
+    __shared__ float red[DW][16];
+    __shared__ float sred[DW];
+    const VbDecState st = *p.st;
+    if (st.eos) return;
+    const int NT = DEC_DIM / 8;                          /* 384 */
+    float xr[8];
+    load_x_cols<1>(xr, p.x, NT);
+    rmsnorm_cols<1>(xr, p.attn_norm[layer], nullptr, NT, DEC_DIM, sred);
+    int u0, n; cta_rows(VB_DEC_QKV / 2, u0, n);
+    const int pos = st.pos, slot = st.pos & (VB_KV_SLOTS - 1);
+    float *kdst = p.kv_k + ((size_t)layer * VB_KV_SLOTS + slot) * VB_DEC_KV;
+    float *vdst = p.kv_v + ((size_t)layer * VB_KV_SLOTS + slot) * VB_DEC_KV;
+    const float *inv_freq = p.inv_freq;
+    float *q = p.q;
+    gemv_rows<1, 16>(p.wqkv[layer], DEC_DIM, NT, u0 * 2, n * 2, xr, red,
+        [&](int row, float v, int lane, bool valid) {
+            float other = __shfl_xor_sync(0xffffffffu, v, 1);
+            if (!valid) return;
+            if (row < VB_DEC_Q + VB_DEC_KV) {            /* RoPE on q and k, voxtral_kernels.c:503-526 */
+                int d = (row & (HD - 1)) >> 1;
+                float sn, cs;
+                sincosf((float)pos * inv_freq[d], &sn, &cs);
+                float y = (row & 1) ? (other * sn + v * cs) : (v * cs - other * sn);
+                if (row < VB_DEC_Q) q[row] = y; else kdst[row - VB_DEC_Q] = y;
+            } else {
+                vdst[row - VB_DEC_Q - VB_DEC_KV] = v;
+            }
+        });
+}
+
+/* Split-S GQA attention over the KV ring: warp = (S-group, kv head); the 4 query heads
+ * of a kv head share every K/V row read.  Order-independent online softmax, so the ring
+ * needs no unrolling: valid slots are [0, min(pos+1, 8192)).  (voxtral_kernels.c:412-482) */
+__global__ void __launch_bounds__(DT, 1) k_dec_attn_partial(DecParams p, int layer) {
+    const VbDecState st = *p.st;
+    if (st.eos) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kvh = warp & 7, sub = warp >> 3;
+    const int NS = gridDim.x * NS_PER_CTA, sg = blockIdx.x * NS_PER_CTA + sub;
+    const int n_valid = min(st.pos + 1, VB_KV_SLOTS);
+    const int s0 = (int)((long long)n_valid * sg / NS), s1 = (int)((long long)n_valid * (sg + 1) / NS);
+    const float scale = 1.0f / sqrtf((float)HD);
+
+    float4 qv[4];
+#pragma unroll
+    for (int hq = 0; hq < 4; hq++)
+        qv[hq] = *reinterpret_cast<const float4 *>(p.q + (kvh * 4 + hq) * HD + lane * 4);
+    float m[4], l[4]; float4 o[4];
+#pragma unroll
+    for (int hq = 0; hq < 4; hq++) { m[hq] = -1e30f; l[hq] = 0.f; o[hq] = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+    const float *kb = p.kv_k + (size_t)layer * VB_KV_SLOTS * VB_DEC_KV + kvh * HD + lane * 4;
+    const float *vb = p.kv_v + (size_t)layer * VB_KV_SLOTS * VB_DEC_KV + kvh * HD + lane * 4;
+    for (int s = s0; s < s1; s++) {
+        float4 k4 = *reinterpret_cast<const float4 *>(kb + (size_t)s * VB_DEC_KV);
+        float4 v4 = *reinterpret_cast<const float4 *>(vb + (size_t)s * VB_DEC_KV);
+        float sc[4];
+#pragma unroll
+        for (int hq = 0; hq < 4; hq++)
+            sc[hq] = qv[hq].x * k4.x + qv[hq].y * k4.y + qv[hq].z * k4.z + qv[hq].w * k4.w;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int hq = 0; hq < 4; hq++) sc[hq] += __shfl_xor_sync(0xffffffffu, sc[hq], off);
+#pragma unroll
+        for (int hq = 0; hq < 4; hq++) {
+            float sv = sc[hq] * scale;
+            float mn = fmaxf(m[hq], sv);
+            float c = expf(m[hq] - mn), pw = expf(sv - mn);
+            l[hq] = l[hq] * c + pw;
+            o[hq].x = o[hq].x * c + pw * v4.x; o[hq].y = o[hq].y * c + pw * v4.y;
+            o[hq].z = o[hq].z * c + pw * v4.z; o[hq].w = o[hq].w * c + pw * v4.w;
+            m[hq] = mn;
+        }
+    }
+#pragma unroll
+    for (int hq = 0; hq < 4; hq++) {
+        int h = kvh * 4 + hq;
+        size_t pi = (size_t)sg * VOX_DEC_HEADS + h;
+        if (lane == 0) { p.part_m[pi] = m[hq]; p.part_l[pi] = l[hq]; }
+        *reinterpret_cast<float4 *>(p.part_o + pi * HD + lane * 4) = o[hq];
+    }
+}
+
+__global__ void __launch_bounds__(HD) k_dec_attn_combine(DecParams p, int NS) {
+    const VbDecState st = *p.st;
+    if (st.eos) return;
+    const int h = blockIdx.x, d = threadIdx.x;
+    float M = -1e30f;
+    for (int i = 0; i < NS; i++) M = fmaxf(M, p.part_m[(size_t)i * VOX_DEC_HEADS + h]);
+    float num = 0.f, den = 0.f;
+    for (int i = 0; i < NS; i++) {
+        size_t pi = (size_t)i * VOX_DEC_HEADS + h;
+        float li = p.part_l[pi];
+        if (li > 0.f) {
+            float w = expf(p.part_m[pi] - M);
+            den = fmaf(w, li, den);
+            num = fmaf(w, p.part_o[pi * HD + d], num);
+        }
+    }
+    p.attn_out[h * HD + d] = den > 0.f ? num / den : 0.f;
+}
+
+__global__ void __launch_bounds__(DT, 1) k_dec_wo(DecParams p, int layer) {
+    __shared__ float red[DW][16];
+    const VbDecState st = *p.st;
+    if (st.eos) return;
+    const int NT = VB_DEC_Q / 8;                         /* 512 */
+    float xr[8];
+    load_x_cols<1>(xr, p.attn_out, NT);
+    int r0, n; cta_rows(DEC_DIM, r0, n);
+    float *x = p.x;
+    gemv_rows<1, 16>(p.wo[layer], VB_DEC_Q, NT, r0, n, xr, red,
+        [&](int row, float v, int, bool valid) { if (valid) x[row] += v; });
+}
+
+__global__ void __launch_bounds__(DT, 1) k_dec_w13(DecParams p, int layer) {
+    __shared__ float red[DW][16];
+    __shared__ float sred[DW];
+    const VbDecState st = *p.st;
+    if (st.eos) return;
+    const int NT = DEC_DIM / 8;
+    float xr[8];
+    load_x_cols<1>(xr, p.x, NT);
+    rmsnorm_cols<1>(xr, p.ffn_norm[layer], p.ada + (size_t)layer * DEC_DIM, NT, DEC_DIM, sred);
+    int u0, n; cta_rows(DEC_HID, u0, n);
+    float *gate = p.gate;
+    gemv_rows<1, 16>(p.w13[layer], DEC_DIM, NT, u0 * 2, n * 2, xr, red,
+        [&](int row, float v, int, bool valid) {
+            float other = __shfl_xor_sync(0xffffffffu, v, 1);
+            if (valid && !(row & 1)) gate[row >> 1] = vb_silu(v) * other;   /* voxtral_decoder.c:682-686 */
+        });
+}
+
+__global__ void __launch_bounds__(DT, 1) k_dec_w2(DecParams p, int layer) {
+    __shared__ float red[DW][4];
+    const VbDecState st = *p.st;
+    if (st.eos) return;
+    const int NT = DEC_HID / 8 / 3;                      /* 384, 3 chunks per thread */
+    float xr[24];
+    load_x_cols<3>(xr, p.gate, NT);
+    int r0, n; cta_rows(DEC_DIM, r0, n);
+    float *x = p.x;
+    gemv_rows<3, 4>(p.w2[layer], DEC_HID, NT, r0, n, xr, red,
+        [&](int row, float v, int, bool valid) { if (valid) x[row] += v; });
+}
+
+__device__ __forceinline__ unsigned long long pack_cand(float v, int idx) {
+    /* order-preserving float key in the high word, inverted index in the low word:
+     * max() over packed values = largest value, ties -> smallest index (voxtral_decoder.c:697-704) */
+    unsigned int u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx);
+}
+
+__global__ void __launch_bounds__(DT, 1) k_dec_logits(DecParams p) {
+    __shared__ float red[DW][16];
+    __shared__ float sred[DW];
+    const VbDecState st = *p.st;
+    if (st.eos) return;
+    const int NT = DEC_DIM / 8;
+    float xr[8];
+    load_x_cols<1>(xr, p.x, NT);
+    rmsnorm_cols<1>(xr, p.final_norm, nullptr, NT, DEC_DIM, sred);
+    int r0, n; cta_rows(VOX_VOCAB_SIZE, r0, n);
+    float *logits = p.logits;
+    unsigned long long best = 0ull;
+    gemv_rows<1, 16>(p.tok_emb, DEC_DIM, NT, r0, n, xr, red,
+        [&](int row, float v, int, bool valid) {
+            if (!valid) return;
+            logits[row] = v;
+            unsigned long long c = pack_cand(v, row);
+            if (c > best) best = c;
+        });
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            if (other > best) best = other;
+        }
+        if (threadIdx.x == 0) p.argmax[blockIdx.x] = best;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dec_finish(DecParams p, int n_cands) {
+    __shared__ unsigned long long sh[8];
+    VbDecState st = *p.st;
+    if (st.eos) return;
+    unsigned long long best = 0ull;
+    for (int i = threadIdx.x; i < n_cands; i += 256) { unsigned long long c = p.argmax[i]; if (c > best) best = c; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other > best) best = other;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) if (sh[i] > best) best = sh[i];
+        int tok = (int)(0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFull));
+        p.tokens[st.n_out] = tok;
+        st.n_out += 1; st.token = tok; st.pos += 1; st.adapter_row += 1;
+        if (tok == VB_TOKEN_EOS) st.eos = 1;
+        *p.st = st;
+    }
+}
+
+/* Standalone GEMV used by the host-pointer parity seam (vox_linear*_bf16 with seq_len == 1):
+ * exercises the very same gemv_rows core as the decode step. */
+template <int CPT>
+__global__ void __launch_bounds__(DT, 1)
+k_gemv_generic(float *__restrict__ y, const float *__restrict__ x, const uint16_t *__restrict__ W,
+               const float *__restrict__ bias, int K, int N, int NT) {
+    __shared__ float red[DW][8];
+    float xr[CPT * 8];
+    load_x_cols<CPT>(xr, x, NT);
+    int r0, n; cta_rows(N, r0, n);
+    gemv_rows<CPT, 8>(W, K, NT, r0, n, xr, red,
+        [&](int row, float v, int, bool valid) { if (valid) y[row] = bias ? v + bias[row] : v; });
+}
+
+/* ---------------------------------------------------------------- host side */
+static DecParams make_params(VbEngine *e, int use_embed_kernel) {
+    DecParams p;
+    memset(&p, 0, sizeof p);
+    p.tok_emb = e->d_tok_emb;
+    for (int l = 0; l < VOX_DEC_LAYERS; l++) {
+        p.wqkv[l] = e->dec[l].wqkv; p.wo[l] = e->dec[l].wo; p.w13[l] = e->dec[l].w13; p.w2[l] = e->dec[l].w2;
+        p.attn_norm[l] = e->dec[l].attn_norm; p.ffn_norm[l] = e->dec[l].ffn_norm;
+    }
+    p.ada = e->d_ada_scale; p.final_norm = e->d_dec_norm; p.inv_freq = e->d_dec_inv_freq;
+    p.kv_k = e->d_kv_k; p.kv_v = e->d_kv_v;
+    p.x = e->d_x; p.q = e->d_q; p.attn_out = e->d_attn_out; p.gate = e->d_gate; p.logits = e->d_logits;
+    p.part_m = e->d_part_m; p.part_l = e->d_part_l; p.part_o = e->d_part_o;
+    p.argmax = e->d_argmax; p.st = e->d_state;
+    p.adapter_pp = (const float *const *)(e->d_state + 1);   /* pointer slot lives right after the state */
+    p.tokens = e->d_tokens;
+    p.use_embed_kernel = use_embed_kernel;
+    return p;
+}
+
+extern "C" void vb_decoder_free(VbEngine *e) {
+    if (e->h_tokens_pinned) { cudaFreeHost(e->h_tokens_pinned); e->h_tokens_pinned = NULL; }
+}
+
+extern "C" int vb_decoder_alloc(VbEngine *e) {
+    if (e->d_kv_k) return 0;
+    const size_t weight_bytes_before = e->weight_bytes;     /* activations/KV are not "weights" */
+    size_t kv = (size_t)VOX_DEC_LAYERS * VB_KV_SLOTS * VB_DEC_KV * sizeof(float);
+    e->d_kv_k = (float *)vb_dev_alloc_owned(e, kv);
+    e->d_kv_v = (float *)vb_dev_alloc_owned(e, kv);
+    e->kv_bytes = 2 * kv;
+    VB_CUDA_OK(cudaMemsetAsync(e->d_kv_k, 0, kv, e->stream));
+    VB_CUDA_OK(cudaMemsetAsync(e->d_kv_v, 0, kv, e->stream));
+    e->d_state = (VbDecState *)vb_dev_alloc_owned(e, sizeof(VbDecState) + 64);
+    VB_CUDA_OK(cudaMemsetAsync(e->d_state, 0, sizeof(VbDecState) + 64, e->stream));
+    e->d_x = (float *)vb_dev_alloc_owned(e, DEC_DIM * 4);
+    e->d_q = (float *)vb_dev_alloc_owned(e, VB_DEC_Q * 4);
+    e->d_attn_out = (float *)vb_dev_alloc_owned(e, VB_DEC_Q * 4);
+    e->d_gate = (float *)vb_dev_alloc_owned(e, DEC_HID * 4);
+    e->d_logits = (float *)vb_dev_alloc_owned(e, (size_t)VOX_VOCAB_SIZE * 4);
+    int NS = e->sm_count * NS_PER_CTA;
+    e->d_part_m = (float *)vb_dev_alloc_owned(e, (size_t)NS * VOX_DEC_HEADS * 4);
+    e->d_part_l = (float *)vb_dev_alloc_owned(e, (size_t)NS * VOX_DEC_HEADS * 4);
+    e->d_part_o = (float *)vb_dev_alloc_owned(e, (size_t)NS * VOX_DEC_HEADS * HD * 4);
+    e->d_argmax = (unsigned long long *)vb_dev_alloc_owned(e, (size_t)e->sm_count * 8);
+    e->tokens_cap = 65536;
+    e->d_tokens = (int *)vb_dev_alloc_owned(e, (size_t)e->tokens_cap * 4);
+    VB_CUDA_OK(cudaMallocHost((void **)&e->h_tokens_pinned, (size_t)e->tokens_cap * 4));
+    e->d_embed_in = (float *)vb_dev_alloc_owned(e, DEC_DIM * 4);
+    e->weight_bytes = weight_bytes_before;
+    return 0;
+}
+
+/* Enqueue the kernels of one decode step on e->stream. */
+static void enqueue_step(VbEngine *e, const DecParams &p) {
+    const int G = e->sm_count;
+    cudaStream_t s = e->stream;
+    if (p.use_embed_kernel) k_dec_embed<<<(DEC_DIM + 255) / 256, 256, 0, s>>>(p);
+    for (int l = 0; l < VOX_DEC_LAYERS; l++) {
+        k_dec_qkv<<<G, DT, 0, s>>>(p, l);
+        k_dec_attn_partial<<<G, DT, 0, s>>>(p, l);
+        k_dec_attn_combine<<<VOX_DEC_HEADS, HD, 0, s>>>(p, G * NS_PER_CTA);
+        k_dec_wo<<<G, DT, 0, s>>>(p, l);
+        k_dec_w13<<<G, DT, 0, s>>>(p, l);
+        k_dec_w2<<<G, DT, 0, s>>>(p, l);
+    }
+    k_dec_logits<<<G, DT, 0, s>>>(p);
+    k_dec_finish<<<1, 256, 0, s>>>(p, G);
+}
+#define STEP_KERNELS (VOX_DEC_LAYERS * 6 + 2)
+
+static void set_state(VbEngine *e, int pos, int token, int adapter_row, const float *d_adapter) {
+    struct { VbDecState st; const float *adapter; } h;
+    memset(&h, 0, sizeof h);
+    h.st.pos = pos; h.st.token = token; h.st.adapter_row = adapter_row;
+    h.adapter = d_adapter;
+    VB_CUDA_OK(cudaMemcpyAsync(e->d_state, &h, sizeof h, cudaMemcpyHostToDevice, e->stream));
+    VB_CUDA_OK(cudaStreamSynchronize(e->stream));   /* h is on the stack */
+}
+
+extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps,
+                                    int prev_token, int pos, int *out_tokens_host) {
+    if (n_steps <= 0) return 0;
+    vb_decoder_alloc(e);
+    int done = 0;
+    double total_ms = 0;
+    while (done < n_steps) {
+        int chunk = n_steps - done;
+        if (chunk > e->tokens_cap) chunk = e->tokens_cap;
+        set_state(e, pos + done, prev_token, adapter_row + done, d_adapter);
+        if (!e->step_graph_ready) {
+            DecParams p = make_params(e, 1);
+            cudaGraph_t g;
+            VB_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            enqueue_step(e, p);
+            VB_CUDA_OK(cudaStreamEndCapture(e->stream, &g));
+            VB_CUDA_OK(cudaGraphInstantiate(&e->step_graph, g, 0));
+            VB_CUDA_OK(cudaGraphDestroy(g));
+            e->step_graph_ready = 1;
+        }
+        VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+        for (int i = 0; i < chunk; i++) VB_CUDA_OK(cudaGraphLaunch(e->step_graph, e->stream));
+        VB_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+        VbDecState st;
+        VB_CUDA_OK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream));
+        VB_CUDA_OK(cudaStreamSynchronize(e->stream));
+        VB_CUDA_OK(cudaMemcpy(e->h_tokens_pinned, e->d_tokens, (size_t)st.n_out * 4, cudaMemcpyDeviceToHost));
+        float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); total_ms += ms;
+        e->launches += (unsigned long long)st.n_out * STEP_KERNELS;
+        memcpy(out_tokens_host + done, e->h_tokens_pinned, (size_t)st.n_out * 4);
+        done += st.n_out;
+        if (st.n_out > 0) prev_token = e->h_tokens_pinned[st.n_out - 1];
+        if (st.eos || st.n_out < chunk) break;
+    }
+    e->last_decode_ms = total_ms; e->last_decode_steps = done;
+    e->total_decode_ms += total_ms; e->total_decode_steps += done;
+    return done;
+}
+
+/* One step from an explicit input embedding (vox_decoder_forward semantics). */
+extern "C" int vb_decoder_step_from_embed(VbEngine *e, const float *d_embed, int pos, float *logits_host) {
+    vb_decoder_alloc(e);
+    set_state(e, pos, 0, 0, nullptr);
+    VB_CUDA_OK(cudaMemcpyAsync(e->d_x, d_embed, DEC_DIM * 4, cudaMemcpyDeviceToDevice, e->stream));
+    DecParams p = make_params(e, 0);
+    enqueue_step(e, p);
+    VB_CUDA_OK(cudaGetLastError());
+    e->launches += STEP_KERNELS - 1;
+    int tok = 0;
+    VB_CUDA_OK(cudaMemcpyAsync(&tok, e->d_tokens, 4, cudaMemcpyDeviceToHost, e->stream));
+    if (logits_host)
+        VB_CUDA_OK(cudaMemcpyAsync(logits_host, e->d_logits, (size_t)VOX_VOCAB_SIZE * 4, cudaMemcpyDeviceToHost, e->stream));
+    VB_CUDA_OK(cudaStreamSynchronize(e->stream));
+    return tok;
+}
+
+extern "C" void vb_gemv_bf16_dev(VbEngine *e, float *y, const float *x, const uint16_t *W, const float *bias, int K, int N) {
+    int chunks = K / 8, cpt = 1;
+    while (cpt <= 4 && (chunks % cpt || chunks / cpt > DT)) cpt++;
+    if (K % 8 || cpt > 4) { fprintf(stderr, "voxtral_b200: GEMV K=%d unsupported\n", K); abort(); }
+    int NT = chunks / cpt, G = e->sm_count;
+    switch (cpt) {
+    case 1: k_gemv_generic<1><<<G, DT, 0, e->stream>>>(y, x, W, bias, K, N, NT); break;
+    case 2: k_gemv_generic<2><<<G, DT, 0, e->stream>>>(y, x, W, bias, K, N, NT); break;
+    case 3: k_gemv_generic<3><<<G, DT, 0, e->stream>>>(y, x, W, bias, K, N, NT); break;
+    case 4: k_gemv_generic<4><<<G, DT, 0, e->stream>>>(y, x, W, bias, K, N, NT); break;
+    }
+    VB_CUDA_OK(cudaGetLastError());
+    vb_launch_count(e, 1);
+}
+
+/* Prefill: seq_len prompt embeddings through the 26 layers, filling the KV ring; no logits
+ * (voxtral_decoder.c:410-558). */
+extern "C" void vb_decoder_prefill_dev(VbEngine *e, const float *d_embeds, int n, int start_pos) {
+    if (n <= 0) return;
+    vb_decoder_alloc(e);
+    if (start_pos + n > VB_KV_SLOTS) {
+        fprintf(stderr, "voxtral_b200: prefill of %d tokens at position %d would wrap the KV ring\n", n, start_pos);
+        abort();
+    }
+    float *x = vb_ws(e, 0, (size_t)n * DEC_DIM * 4);
+    float *xn = vb_ws(e, 1, (size_t)n * DEC_DIM * 4);
+    float *qkv = vb_ws(e, 2, (size_t)n * VB_DEC_QKV * 4);
+    float *att = vb_ws(e, 3, (size_t)n * VB_DEC_Q * 4);
+    float *g = vb_ws(e, 4, (size_t)n * DEC_HID * 4);
+    VB_CUDA_OK(cudaMemcpyAsync(x, d_embeds, (size_t)n * DEC_DIM * 4, cudaMemcpyDeviceToDevice, e->stream));
+    const float scale = 1.0f / sqrtf((float)HD);
+    for (int l = 0; l < VOX_DEC_LAYERS; l++) {
+        float *kl = e->d_kv_k + (size_t)l * VB_KV_SLOTS * VB_DEC_KV;
+        float *vl = e->d_kv_v + (size_t)l * VB_KV_SLOTS * VB_DEC_KV;
+        vb_rmsnorm_rows(e, xn, x, e->dec[l].attn_norm, nullptr, n, DEC_DIM, VOX_DEC_NORM_EPS);
+        vb_gemm_bf16w(e, xn, DEC_DIM, e->dec[l].wqkv, nullptr, qkv, VB_DEC_QKV, n, VB_DEC_QKV, DEC_DIM, VB_EPI_STORE);
+        vb_rope_split(e, qkv, VB_DEC_QKV, n, VOX_DEC_HEADS, VOX_DEC_KV_HEADS, HD, e->d_dec_inv_freq, start_pos,
+                      kl, vl, start_pos, VB_KV_SLOTS - 1);
+        vb_attention_rows(e, att, VB_DEC_Q, qkv, VB_DEC_QKV, kl, vl, VB_DEC_KV, n, start_pos + n,
+                          VOX_DEC_HEADS, VOX_DEC_KV_HEADS, HD, scale, VOX_DEC_WINDOW, start_pos);
+        vb_gemm_bf16w(e, att, VB_DEC_Q, e->dec[l].wo, nullptr, x, DEC_DIM, n, DEC_DIM, VB_DEC_Q, VB_EPI_RESIDUAL);
+        vb_rmsnorm_rows(e, xn, x, e->dec[l].ffn_norm, e->d_ada_scale + (size_t)l * DEC_DIM, n, DEC_DIM, VOX_DEC_NORM_EPS);
+        vb_gemm_bf16w(e, xn, DEC_DIM, e->dec[l].w13, nullptr, g, DEC_HID, n, 2 * DEC_HID, DEC_DIM, VB_EPI_SWIGLU);
+        vb_gemm_bf16w(e, g, DEC_HID, e->dec[l].w2, nullptr, x, DEC_DIM, n, DEC_DIM, DEC_HID, VB_EPI_RESIDUAL);
+    }
+}

@@ -1,0 +1,172 @@
+/*
+ * vb_engine.h -- internal layout of the B200 engine (not part of the C ABI).
+ *
+ * One VbEngine per vox_ctx_t; the public struct is the first member so the
+ * vox_ctx_t* handed to callers is also the engine pointer (the reference's
+ * Metal backend keys its GPU state off the same struct, voxtral_metal.m:111-147).
+ *
+ * HBM layout (all allocations are made once in vox_load / first use):
+ *   weights   bf16, row-major [out,in] exactly as in the checkpoint, except
+ *             - decoder/encoder wq|wk|wv are stored back to back as one
+ *               [q+k+v, in] matrix (one GEMV/GEMM instead of three),
+ *             - w1|w3 are row-interleaved (g0,u0,g1,u1,...) so SiLU(g)*u is an
+ *               epilogue of the producing kernel.
+ *   small f32 tensors (norms, biases, conv weights, ada_scale, RoPE inv_freq)
+ *   decoder KV   f32 ring  [26][8192][1024] x {K,V}   (slot = position & 8191)
+ *   encoder KV   f32 tail  [32][750][2048]  x {K,V}   (last 750 positions per layer)
+ *   activations  f32, sized on demand for the largest M seen.
+ */
+#ifndef VB_ENGINE_H
+#define VB_ENGINE_H
+
+#include "voxtral_b200.h"
+
+#include <cuda_runtime_api.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define VB_ENC_QKV   (3 * VOX_ENC_HEADS * VOX_ENC_HEAD_DIM)            /* 6144 */
+#define VB_ENC_ATT   (VOX_ENC_HEADS * VOX_ENC_HEAD_DIM)                /* 2048 */
+#define VB_DEC_Q     (VOX_DEC_HEADS * VOX_DEC_HEAD_DIM)                /* 4096 */
+#define VB_DEC_KV    (VOX_DEC_KV_HEADS * VOX_DEC_HEAD_DIM)             /* 1024 */
+#define VB_DEC_QKV   (VB_DEC_Q + 2 * VB_DEC_KV)                        /* 6144 */
+#define VB_KV_SLOTS  VOX_DEC_WINDOW                                    /* 8192 */
+#define VB_TOKEN_EOS 2
+#define VB_WS_SLOTS  24   /* 0-11: model blocks (see vb_encoder.cu), 12-23: stream pipeline */
+
+#define VB_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) {                 \
+    fprintf(stderr, "voxtral_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__),        \
+            __FILE__, __LINE__, cudaGetErrorString(e__)); abort(); } } while (0)
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    const uint16_t *wqkv, *wo, *w13, *w2;       /* bf16 device */
+    const float *attn_norm, *ffn_norm;          /* f32 device  */
+} VbDecLayerDev;
+
+typedef struct {
+    const uint16_t *wqkv, *wo, *w13, *w2;
+    const float *bqkv;                          /* [6144] = [wq_bias | 0 | wv_bias] */
+    const float *bo, *b2;
+    const float *attn_norm, *ffn_norm;
+} VbEncLayerDev;
+
+/* Device-side autoregressive state: lives in HBM, advanced by the decode kernels. */
+typedef struct {
+    int pos;            /* logical position of the token about to be processed */
+    int token;          /* previous token id (input of the next step) */
+    int eos;            /* set once EOS was emitted: later steps are no-ops */
+    int n_out;          /* tokens written to out_tokens so far in this call */
+    int adapter_row;    /* row of d_adapter consumed by the next step */
+    int pad[3];
+} VbDecState;
+
+typedef struct VbHostMirror { const void *host; size_t bytes; void *dev; } VbHostMirror;
+
+typedef struct VbEngine {
+    vox_ctx_t pub;                              /* MUST be first */
+
+    int device, sm_count, cc_major, cc_minor;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    cudaEvent_t ev_user0, ev_user1;             /* vox_cuda_timer_* */
+
+    /* ---- weights ---- */
+    uint16_t *d_tok_emb;
+    VbDecLayerDev dec[VOX_DEC_LAYERS];
+    float *d_dec_norm;
+    float *d_ada_scale;                         /* [26][3072] */
+    float *d_dec_inv_freq;                      /* [64]  */
+    VbEncLayerDev enc[VOX_ENC_LAYERS];
+    float *d_enc_norm;
+    float *d_enc_inv_freq;                      /* [32]  */
+    uint16_t *d_conv0_wk, *d_conv1_wk;          /* conv weights re-ordered to [cout][k][cin], bf16 (exact) */
+    float *d_conv0_b, *d_conv1_b;
+    uint16_t *d_adapter0, *d_adapter1;
+    size_t weight_bytes;
+
+    VbHostMirror *mirrors; int n_mirrors, cap_mirrors;
+    void **owned; int n_owned, cap_owned;       /* device allocations freed in vox_free */
+
+    /* ---- decoder state ---- */
+    float *d_kv_k, *d_kv_v;                     /* [26][8192][1024] */
+    size_t kv_bytes;
+    VbDecState *d_state;
+    float *d_x, *d_q, *d_attn_out, *d_gate, *d_logits;
+    float *d_part_m, *d_part_l, *d_part_o;      /* split-S attention partials */
+    unsigned long long *d_argmax;               /* per-CTA packed (value,index) */
+    int *d_tokens;  int tokens_cap;
+    int *h_tokens_pinned;
+    float *d_embed_in;                          /* [3072] staging for the host-pointer API */
+    cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
+    int step_graph_ready;
+
+    /* ---- M>1 scratch (prefill / encoder / adapter) ---- */
+    float *ws[VB_WS_SLOTS]; size_t ws_bytes[VB_WS_SLOTS];         /* grow-on-demand workspaces */
+    float *d_enc_tail_k, *d_enc_tail_v;         /* [32][750][2048] */
+    int enc_tail_len;                           /* rows valid in the tail (<=750) */
+
+    /* ---- statistics ---- */
+    unsigned long long launches;
+    double last_decode_ms; int last_decode_steps;
+    double last_encoder_ms; int last_encoder_positions;
+    double last_mel_ms;
+    double total_decode_ms; long long total_decode_steps;
+    double total_encoder_ms; long long total_encoder_positions;
+} VbEngine;
+
+static inline VbEngine *vb_engine(vox_ctx_t *ctx) { return (VbEngine *)ctx; }
+
+/* vb_runtime.cu */
+int   vb_device_init(VbEngine *e);              /* picks the device, creates the stream; -1 if no sm_100 GPU */
+void  vb_device_shutdown(VbEngine *e);
+void *vb_dev_alloc(size_t bytes);
+void *vb_dev_alloc_owned(VbEngine *e, size_t bytes);                    /* freed at shutdown */
+void *vb_dev_upload(VbEngine *e, const void *host, size_t bytes);       /* alloc + H2D + register mirror */
+void  vb_register_mirror(VbEngine *e, const void *host, size_t bytes, void *dev);
+void *vb_find_mirror(VbEngine *e, const void *host);
+float *vb_ws(VbEngine *e, int slot, size_t bytes);                      /* workspace, grown on demand */
+void  vb_require_gpu(const char *what);         /* aborts loudly if the CUDA device is missing */
+VbEngine *vb_default_engine(void);              /* engine used by the host-pointer kernel wrappers */
+void  vb_set_default_engine(VbEngine *e);
+
+/* vb_decode.cu */
+int  vb_decoder_alloc(VbEngine *e);
+void vb_decoder_free(VbEngine *e);
+void vb_decoder_reset(VbEngine *e);
+void vb_decoder_set_state(VbEngine *e, int pos, int token, int adapter_row);
+int  vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps,
+                          int prev_token, int pos, int *out_tokens_host);
+int  vb_decoder_step_from_embed(VbEngine *e, const float *d_embed, int pos, float *logits_host);
+void vb_decoder_prefill_dev(VbEngine *e, const float *d_embeds, int n, int start_pos);
+
+/* vb_encoder.cu */
+void vb_encoder_layers_dev(VbEngine *e, float *d_x, int new_len, int cache_len, int logical_start, int update_tail);
+void vb_adapter_dev(VbEngine *e, const float *d_enc, int enc_len, float *d_out);
+void vb_conv_view_dev(VbEngine *e, const float *in, int cin, int stride, int n_out,
+                      const uint16_t *w_kc, const float *bias, float *out, int cout);
+
+/* vb_mel.cu */
+vox_mel_ctx_t *vb_mel_ctx_init_on(VbEngine *e, int left_pad_samples);
+int    vb_mel_feed_zeros(vox_mel_ctx_t *c, int n);
+int    vb_mel_feed_device(vox_mel_ctx_t *c, const float *d_samples, int n);
+float *vb_mel_dev_frames(vox_mel_ctx_t *c, int *n_frames, int *frame_offset);
+
+/* vb_stream_dev.cu */
+void vb_d2d(VbEngine *e, void *dst, const void *src, size_t bytes);
+void vb_dzero(VbEngine *e, void *dst, size_t bytes);
+void vb_h2d(VbEngine *e, void *dst, const void *src, size_t bytes);
+void vb_d2h_sync(VbEngine *e, void *dst, const void *src, size_t bytes);
+void vb_sync(VbEngine *e);
+void vb_build_prompt_dev(VbEngine *e, float *d_out, const float *d_adapter, int n, int bos, int pad);
+void vb_conv_stem_full_dev(VbEngine *e, const float *d_mel, int mel_frames, float *d_out, int *out_len);
+void vb_gemv_bf16_dev(VbEngine *e, float *y, const float *x, const uint16_t *W, const float *bias, int K, int N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
