@@ -363,6 +363,11 @@ typedef struct {
 } vox_cuda_info_t;
 int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out);
 const char *vox_cuda_version(void);
+/* Decode driver: 0 = auto (persistent megakernel when the device supports cooperative launch),
+ * 1 = one kernel per phase replayed as a CUDA graph, 2 = persistent megakernel.  Both produce the same
+ * tokens; the graph path exists for validation and profiling of individual phases. */
+void vox_cuda_set_decode_mode(vox_ctx_t *ctx, int mode);
+
 /* Forget both KV caches (decoder ring positions and encoder tail), like a freshly loaded ctx. */
 void vox_cuda_reset_caches(vox_ctx_t *ctx);
 

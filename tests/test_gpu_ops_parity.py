@@ -142,7 +142,11 @@ def test_rope(vb, ref, hd, heads, pos0):
     fa, fb = np.empty((seq, hd), np.float32), np.empty((seq, hd), np.float32)
     vb.lib().vox_compute_rope_freqs(P(fa), pos.ctypes.data_as(C.POINTER(C.c_int)), seq, hd, 1e6)
     ref.L.vox_compute_rope_freqs(P(fb), pos.ctypes.data_as(C.POINTER(C.c_int)), seq, hd, 1e6)
-    close(fa, fb, 1e-6)
+    # cos/sin of angle = (float)pos * freq: one ulp of the f32 ANGLE is pos*2^-23 rad, and the reference
+    # build (-ffast-math, libmvec _ZGVdN8vv_powf/_ZGVdN8v_cosf) rounds freq differently from scalar libm, so
+    # the tables agree to a few angle-ulps, not to 1e-6, at large positions (SURVEY.md section 7 hard part 6).
+    tol = max(2e-6, 4.0 * (pos0 + seq) * 2.0 ** -23)
+    assert float(np.abs(fa - fb).max()) <= tol
     x = rng.normal(size=(seq, heads * hd)).astype(np.float32)
     a, b = x.copy(), x.copy()
     vb.lib().vox_apply_rope(P(a), P(fb), seq, heads, hd)
@@ -195,12 +199,13 @@ def test_mel_batch_and_stream(vb, ref):
     assert n1.value == n2.value == 200
     a = np.ctypeslib.as_array(pa, shape=(n1.value, 128)).copy()
     b = np.ctypeslib.as_array(pb, shape=(n2.value, 128)).copy()
-    # log-mel values are O(1); 1e-4 abs covers log10 of tiny, clamped bins computed in another order
-    assert np.abs(a - b).max() < 2e-4, np.abs(a - b).max()
+    # log-mel values are O(1) and stored as (log10(p)+4)/4; bins whose power is a near-cancelling sum (1e-8 of the
+    # frame energy) move by ~1e-3 relative under a different f32 summation order -> 5e-4 absolute after the log
+    assert np.abs(a - b).max() < 5e-4, np.abs(a - b).max()
     # streaming: same frames regardless of how the audio is chunked; equals the reference stream mel
     sa = _mel_stream(vb.lib(), pcm, [pcm.size], None)
     sb = _mel_stream(ref.L, pcm, [pcm.size], None)
     sc = _mel_stream(vb.lib(), pcm, [1000, 160, 1, 7777, pcm.size], None)
     assert sa.shape == sb.shape == sc.shape
-    assert np.abs(sa - sb).max() < 2e-4
+    assert np.abs(sa - sb).max() < 5e-4
     assert np.array_equal(sa, sc)

@@ -54,6 +54,19 @@ def test_oneshot_tokens_match_reference(engine):
     check_against(g, ids, text)
 
 
+def test_graph_and_megakernel_decode_agree(engine):
+    """The per-phase CUDA-graph driver and the persistent megakernel are two schedules of the same math."""
+    pcm = read_wav_f32(synth_wav(2))
+    g = golden("synth_s2_oneshot")
+    out = {}
+    for mode in ("graph", "mega"):
+        engine.set_decode_mode(mode)
+        out[mode], text, _ = run_stream(engine, pcm)
+        check_against(g, out[mode], text)
+    engine.set_decode_mode("auto")
+    assert out["graph"].tolist() == out["mega"].tolist()
+
+
 def test_chunked_1s_tokens_match_reference(engine):
     g = golden("synth_s2_chunk1s")
     pcm = read_wav_f32(synth_wav(2))

@@ -92,7 +92,7 @@ def lib():
         "vox_tokenizer_load": (vp, [C.c_char_p]), "vox_tokenizer_free": (None, [vp]),
         "vox_tokenizer_decode": (C.c_char_p, [vp, i]),
         "vox_cuda_get_info": (i, [vp, C.POINTER(CudaInfo)]), "vox_cuda_version": (C.c_char_p, []),
-        "vox_cuda_reset_caches": (None, [vp]),
+        "vox_cuda_reset_caches": (None, [vp]), "vox_cuda_set_decode_mode": (None, [vp, i]),
         "vox_cuda_stream_feed_device": (i, [vp, vp, i]),
         "vox_cuda_malloc": (vp, [vp, C.c_size_t]), "vox_cuda_free": (None, [vp, vp]),
         "vox_cuda_memcpy_h2d": (i, [vp, vp, vp, C.c_size_t]), "vox_cuda_memcpy_d2h": (i, [vp, vp, vp, C.c_size_t]),
@@ -176,6 +176,9 @@ class Engine:
 
     def timer_stop_ms(self):
         return lib().vox_cuda_timer_stop_ms(self.ctx)
+
+    def set_decode_mode(self, mode):
+        lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "mega": 2}[mode])
 
     def reset_caches(self):
         lib().vox_cuda_reset_caches(self.ctx)

@@ -23,175 +23,8 @@
  * are in flight per thread.  Partial sums are combined with a warp transpose-
  * reduce (R values in ~R shuffles) and one shared-memory pass.
  */
-#include "vb_ops.cuh"
+#include "vb_decode_common.cuh"
 #include <string.h>
-
-#define DT 512                       /* threads per decode CTA */
-#define DW (DT / 32)
-#define DEC_DIM   VOX_DEC_DIM
-#define DEC_HID   VOX_DEC_HIDDEN
-#define HD        VOX_DEC_HEAD_DIM
-#define NS_PER_CTA 2                 /* split-S groups per CTA in decode attention */
-
-struct DecParams {
-    const uint16_t *tok_emb;
-    const uint16_t *wqkv[VOX_DEC_LAYERS], *wo[VOX_DEC_LAYERS], *w13[VOX_DEC_LAYERS], *w2[VOX_DEC_LAYERS];
-    const float *attn_norm[VOX_DEC_LAYERS], *ffn_norm[VOX_DEC_LAYERS];
-    const float *ada;               /* [26][3072] */
-    const float *final_norm;
-    const float *inv_freq;          /* [64] */
-    float *kv_k, *kv_v;             /* [26][8192][1024] */
-    float *x, *q, *attn_out, *gate, *logits;
-    float *part_m, *part_l, *part_o;
-    unsigned long long *argmax;
-    VbDecState *st;
-    const float *const *adapter_pp; /* device slot holding the adapter base pointer */
-    int *tokens;
-    int use_embed_kernel;
-};
-
-/* ---------------------------------------------------------------- helpers */
-__device__ __forceinline__ uint4 ldg_stream16(const void *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ float dot8(const uint4 w, const float *x, float acc) {
-    acc = fmaf(vb_bf16_lo(w.x), x[0], acc); acc = fmaf(vb_bf16_hi(w.x), x[1], acc);
-    acc = fmaf(vb_bf16_lo(w.y), x[2], acc); acc = fmaf(vb_bf16_hi(w.y), x[3], acc);
-    acc = fmaf(vb_bf16_lo(w.z), x[4], acc); acc = fmaf(vb_bf16_hi(w.z), x[5], acc);
-    acc = fmaf(vb_bf16_lo(w.w), x[6], acc); acc = fmaf(vb_bf16_hi(w.w), x[7], acc);
-    return acc;
-}
-
-template <int R> struct Log2;
-template <> struct Log2<4>  { static const int v = 2; };
-template <> struct Log2<8>  { static const int v = 3; };
-template <> struct Log2<16> { static const int v = 4; };
-template <> struct Log2<32> { static const int v = 5; };
-
-/* Sum v[i] over the 32 lanes for all i<R with ~R shuffles.  Returns the total of
- * index (lane >> (5-log2 R)); lanes sharing that index hold the same value. */
-template <int R>
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[R], int lane) {
-    int off = 16;
-#pragma unroll
-    for (int n = R; n > 1; n >>= 1, off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; i++) {
-            float send = upper ? v[i] : v[i + n / 2];
-            float keep = upper ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    float r = v[0];
-#pragma unroll
-    for (int o = (16 >> Log2<R>::v); o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    return r;
-}
-
-/* Thread t (< NT) loads its CPT*8 activation values: chunk c covers k = (c*NT+t)*8 .. +7 */
-template <int CPT>
-__device__ __forceinline__ void load_x_cols(float (&xr)[CPT * 8], const float *__restrict__ x, int NT) {
-    const int t = threadIdx.x;
-#pragma unroll
-    for (int c = 0; c < CPT; c++) {
-        if (t < NT) {
-            const float4 *p = reinterpret_cast<const float4 *>(x + (size_t)(c * NT + t) * 8);
-            float4 a = p[0], b = p[1];
-            xr[c * 8 + 0] = a.x; xr[c * 8 + 1] = a.y; xr[c * 8 + 2] = a.z; xr[c * 8 + 3] = a.w;
-            xr[c * 8 + 4] = b.x; xr[c * 8 + 5] = b.y; xr[c * 8 + 6] = b.z; xr[c * 8 + 7] = b.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++) xr[c * 8 + j] = 0.f;
-        }
-    }
-}
-
-/* Block-wide sum (all DT threads call). */
-__device__ __forceinline__ float block_sum(float v, float *red /* [DW] */) {
-    v = vb_warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < DW; i++) t += red[i];
-    return t;
-}
-
-/* RMSNorm of the register-resident vector (voxtral_kernels.c:346-363), optional (1+ada). */
-template <int CPT>
-__device__ __forceinline__ void rmsnorm_cols(float (&xr)[CPT * 8], const float *__restrict__ w,
-                                             const float *__restrict__ ada, int NT, int hidden, float *red) {
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < CPT * 8; j++) ss = fmaf(xr[j], xr[j], ss);
-    float tot = block_sum(ss, red);
-    float rinv = 1.0f / sqrtf(tot / (float)hidden + VOX_DEC_NORM_EPS);
-    const int t = threadIdx.x;
-    if (t < NT) {
-#pragma unroll
-        for (int c = 0; c < CPT; c++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                int k = (c * NT + t) * 8 + j;
-                float v = xr[c * 8 + j] * rinv * w[k];
-                if (ada) v *= (1.0f + ada[k]);
-                xr[c * 8 + j] = v;
-            }
-    }
-}
-
-/* y[row] = W[row,:] . x for rows [row0, row0+nrows); epi(row, value, lane, valid) runs in warp 0. */
-template <int CPT, int R, typename Epi>
-__device__ __forceinline__ void gemv_rows(const uint16_t *__restrict__ W, int K, int NT, int row0, int nrows,
-                                          const float (&xr)[CPT * 8], float (*red)[R], Epi epi) {
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const bool active = t < NT;
-    const uint16_t *wt = W + (size_t)t * 8;
-    for (int rb = 0; rb < nrows; rb += R) {
-        const int nr = min(R, nrows - rb);
-        uint4 w[R][CPT];
-#pragma unroll
-        for (int r = 0; r < R; r++)
-#pragma unroll
-            for (int c = 0; c < CPT; c++) {
-                if (active && r < nr) w[r][c] = ldg_stream16(wt + (size_t)(row0 + rb + r) * K + (size_t)c * NT * 8);
-                else w[r][c] = make_uint4(0u, 0u, 0u, 0u);
-            }
-        float acc[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            float a = 0.f;
-#pragma unroll
-            for (int c = 0; c < CPT; c++) a = dot8(w[r][c], &xr[c * 8], a);
-            acc[r] = a;
-        }
-        float tot = warp_transpose_reduce<R>(acc, lane);
-        if ((lane & ((32 >> Log2<R>::v) - 1)) == 0) red[warp][lane >> (5 - Log2<R>::v)] = tot;
-        __syncthreads();
-        if (warp == 0) {
-            float s = 0.f;
-            if (lane < R) {
-#pragma unroll
-                for (int wv = 0; wv < DW; wv++) s += red[wv][lane];
-            }
-            epi(row0 + rb + lane, s, lane, lane < nr);
-        }
-        __syncthreads();
-    }
-}
-
-__device__ __forceinline__ void cta_rows(int total_units, int &u0, int &n) {
-    /* contiguous, balanced partition of `total_units` over the grid */
-    long long a = (long long)total_units * blockIdx.x / gridDim.x;
-    long long b = (long long)total_units * (blockIdx.x + 1) / gridDim.x;
-    u0 = (int)a; n = (int)(b - a);
-}
 
 /* ---------------------------------------------------------------- kernels */
 __global__ void __launch_bounds__(256) k_dec_embed(DecParams p) {
@@ -290,14 +123,24 @@ __global__ void __launch_bounds__(DT, 1) k_dec_attn_partial(DecParams p, int lay
     }
 }
 
-__global__ void __launch_bounds__(HD) k_dec_attn_combine(DecParams p, int NS) {
+/* Combine the split-S partials: grid = (32 heads, 4 dim-quarters), 512 threads = 32 dims x 16 partial lanes. */
+__global__ void __launch_bounds__(DT) k_dec_attn_combine(DecParams p, int NS) {
+    __shared__ float sm_m[16], sm_num[16][33], sm_den[16][33];
     const VbDecState st = *p.st;
     if (st.eos) return;
-    const int h = blockIdx.x, d = threadIdx.x;
+    const int h = blockIdx.x, dq = blockIdx.y;
+    const int dl = threadIdx.x & 31, pl = threadIdx.x >> 5;          /* dim within quarter, partial lane (= warp) */
+    const int d = dq * 32 + dl;
     float M = -1e30f;
-    for (int i = 0; i < NS; i++) M = fmaxf(M, p.part_m[(size_t)i * VOX_DEC_HEADS + h]);
+    for (int i = threadIdx.x; i < NS; i += DT) M = fmaxf(M, p.part_m[(size_t)i * VOX_DEC_HEADS + h]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    if (dl == 0) sm_m[pl] = M;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; i++) M = fmaxf(M, sm_m[i]);
     float num = 0.f, den = 0.f;
-    for (int i = 0; i < NS; i++) {
+    for (int i = pl; i < NS; i += 16) {
         size_t pi = (size_t)i * VOX_DEC_HEADS + h;
         float li = p.part_l[pi];
         if (li > 0.f) {
@@ -306,7 +149,14 @@ __global__ void __launch_bounds__(HD) k_dec_attn_combine(DecParams p, int NS) {
             num = fmaf(w, p.part_o[pi * HD + d], num);
         }
     }
-    p.attn_out[h * HD + d] = den > 0.f ? num / den : 0.f;
+    sm_num[pl][dl] = num; sm_den[pl][dl] = den;
+    __syncthreads();
+    if (pl == 0) {
+        float n2 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) { n2 += sm_num[i][dl]; d2 += sm_den[i][dl]; }
+        p.attn_out[h * HD + d] = d2 > 0.f ? n2 / d2 : 0.f;
+    }
 }
 
 __global__ void __launch_bounds__(DT, 1) k_dec_wo(DecParams p, int layer) {
@@ -353,14 +203,6 @@ __global__ void __launch_bounds__(DT, 1) k_dec_w2(DecParams p, int layer) {
         [&](int row, float v, int, bool valid) { if (valid) x[row] += v; });
 }
 
-__device__ __forceinline__ unsigned long long pack_cand(float v, int idx) {
-    /* order-preserving float key in the high word, inverted index in the low word:
-     * max() over packed values = largest value, ties -> smallest index (voxtral_decoder.c:697-704) */
-    unsigned int u = __float_as_uint(v);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx);
-}
-
 __global__ void __launch_bounds__(DT, 1) k_dec_logits(DecParams p) {
     __shared__ float red[DW][16];
     __shared__ float sred[DW];
@@ -405,7 +247,7 @@ __global__ void __launch_bounds__(256) k_dec_finish(DecParams p, int n_cands) {
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < 8; i++) if (sh[i] > best) best = sh[i];
-        int tok = (int)(0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFull));
+        int tok = cand_index(best);
         p.tokens[st.n_out] = tok;
         st.n_out += 1; st.token = tok; st.pos += 1; st.adapter_row += 1;
         if (tok == VB_TOKEN_EOS) st.eos = 1;
@@ -428,7 +270,7 @@ k_gemv_generic(float *__restrict__ y, const float *__restrict__ x, const uint16_
 }
 
 /* ---------------------------------------------------------------- host side */
-static DecParams make_params(VbEngine *e, int use_embed_kernel) {
+DecParams vb_make_dec_params(VbEngine *e, int use_embed_kernel) {
     DecParams p;
     memset(&p, 0, sizeof p);
     p.tok_emb = e->d_tok_emb;
@@ -488,7 +330,7 @@ static void enqueue_step(VbEngine *e, const DecParams &p) {
     for (int l = 0; l < VOX_DEC_LAYERS; l++) {
         k_dec_qkv<<<G, DT, 0, s>>>(p, l);
         k_dec_attn_partial<<<G, DT, 0, s>>>(p, l);
-        k_dec_attn_combine<<<VOX_DEC_HEADS, HD, 0, s>>>(p, G * NS_PER_CTA);
+        k_dec_attn_combine<<<dim3(VOX_DEC_HEADS, 4), DT, 0, s>>>(p, G * NS_PER_CTA);
         k_dec_wo<<<G, DT, 0, s>>>(p, l);
         k_dec_w13<<<G, DT, 0, s>>>(p, l);
         k_dec_w2<<<G, DT, 0, s>>>(p, l);
@@ -507,35 +349,59 @@ static void set_state(VbEngine *e, int pos, int token, int adapter_row, const fl
     VB_CUDA_OK(cudaStreamSynchronize(e->stream));   /* h is on the stack */
 }
 
+static int use_mega(VbEngine *e) {
+    if (e->decode_mode == 0) {
+        const char *m = getenv("VOX_CUDA_DECODE");            /* "graph" forces the per-phase CUDA-graph path */
+        e->decode_mode = (m && !strcmp(m, "graph")) ? 1 : 2;
+        if (e->decode_mode == 2 && !vb_decoder_mega_supported(e)) {
+            fprintf(stderr, "voxtral_b200: cooperative megakernel unavailable on this device, using the CUDA-graph path\n");
+            e->decode_mode = 1;
+        }
+    }
+    return e->decode_mode == 2;
+}
+
 extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps,
                                     int prev_token, int pos, int *out_tokens_host) {
     if (n_steps <= 0) return 0;
     vb_decoder_alloc(e);
+    const int mega = use_mega(e);
+    const int max_chunk = mega ? 2048 : e->tokens_cap;          /* bound the lifetime of one persistent launch */
     int done = 0;
     double total_ms = 0;
     while (done < n_steps) {
         int chunk = n_steps - done;
-        if (chunk > e->tokens_cap) chunk = e->tokens_cap;
-        set_state(e, pos + done, prev_token, adapter_row + done, d_adapter);
-        if (!e->step_graph_ready) {
-            DecParams p = make_params(e, 1);
-            cudaGraph_t g;
-            VB_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-            enqueue_step(e, p);
-            VB_CUDA_OK(cudaStreamEndCapture(e->stream, &g));
-            VB_CUDA_OK(cudaGraphInstantiate(&e->step_graph, g, 0));
-            VB_CUDA_OK(cudaGraphDestroy(g));
-            e->step_graph_ready = 1;
+        if (chunk > max_chunk) chunk = max_chunk;
+        if (mega) {
+            VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+            vb_decoder_mega_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
+            VB_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+        } else {
+            set_state(e, pos + done, prev_token, adapter_row + done, d_adapter);
+            if (!e->step_graph_ready) {
+                DecParams p = vb_make_dec_params(e, 1);
+                cudaGraph_t g;
+                VB_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+                enqueue_step(e, p);
+                VB_CUDA_OK(cudaStreamEndCapture(e->stream, &g));
+                VB_CUDA_OK(cudaGraphInstantiate(&e->step_graph, g, 0));
+                VB_CUDA_OK(cudaGraphDestroy(g));
+                e->step_graph_ready = 1;
+            }
+            VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+            for (int i = 0; i < chunk; i++) VB_CUDA_OK(cudaGraphLaunch(e->step_graph, e->stream));
+            VB_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         }
-        VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
-        for (int i = 0; i < chunk; i++) VB_CUDA_OK(cudaGraphLaunch(e->step_graph, e->stream));
-        VB_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         VbDecState st;
         VB_CUDA_OK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream));
-        VB_CUDA_OK(cudaStreamSynchronize(e->stream));
+        cudaError_t serr = cudaStreamSynchronize(e->stream);
+        if (serr != cudaSuccess) {
+            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), mega ? "megakernel" : "graph");
+            abort();
+        }
         VB_CUDA_OK(cudaMemcpy(e->h_tokens_pinned, e->d_tokens, (size_t)st.n_out * 4, cudaMemcpyDeviceToHost));
         float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); total_ms += ms;
-        e->launches += (unsigned long long)st.n_out * STEP_KERNELS;
+        if (!mega) e->launches += (unsigned long long)st.n_out * STEP_KERNELS;
         memcpy(out_tokens_host + done, e->h_tokens_pinned, (size_t)st.n_out * 4);
         done += st.n_out;
         if (st.n_out > 0) prev_token = e->h_tokens_pinned[st.n_out - 1];
@@ -551,7 +417,7 @@ extern "C" int vb_decoder_step_from_embed(VbEngine *e, const float *d_embed, int
     vb_decoder_alloc(e);
     set_state(e, pos, 0, 0, nullptr);
     VB_CUDA_OK(cudaMemcpyAsync(e->d_x, d_embed, DEC_DIM * 4, cudaMemcpyDeviceToDevice, e->stream));
-    DecParams p = make_params(e, 0);
+    DecParams p = vb_make_dec_params(e, 0);
     enqueue_step(e, p);
     VB_CUDA_OK(cudaGetLastError());
     e->launches += STEP_KERNELS - 1;

@@ -102,6 +102,8 @@ typedef struct VbEngine {
     int *d_tokens;  int tokens_cap;
     int *h_tokens_pinned;
     float *d_embed_in;                          /* [3072] staging for the host-pointer API */
+    unsigned int *d_mega_bar;                   /* grid-barrier counter + error word of the persistent kernel */
+    int decode_mode;                            /* 0 = auto, 1 = CUDA-graph phases, 2 = persistent megakernel */
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
 
@@ -143,6 +145,10 @@ int  vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int adapter_row, 
                           int prev_token, int pos, int *out_tokens_host);
 int  vb_decoder_step_from_embed(VbEngine *e, const float *d_embed, int pos, float *logits_host);
 void vb_decoder_prefill_dev(VbEngine *e, const float *d_embeds, int n, int start_pos);
+
+/* vb_decode_mega.cu */
+int  vb_decoder_mega_supported(VbEngine *e);
+int  vb_decoder_mega_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 
 /* vb_encoder.cu */
 void vb_encoder_layers_dev(VbEngine *e, float *d_x, int new_len, int cache_len, int logical_start, int update_tail);

@@ -756,6 +756,10 @@ int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out) {
     return 0;
 }
 
+void vox_cuda_set_decode_mode(vox_ctx_t *ctx, int mode) {
+    if (ctx) vb_engine(ctx)->decode_mode = mode;
+}
+
 void vox_cuda_reset_caches(vox_ctx_t *ctx) {
     if (!ctx) return;
     vb_sync(vb_engine(ctx));
