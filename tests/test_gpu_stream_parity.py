@@ -54,17 +54,17 @@ def test_oneshot_tokens_match_reference(engine):
     check_against(g, ids, text)
 
 
-def test_graph_and_megakernel_decode_agree(engine):
-    """The per-phase CUDA-graph driver and the persistent megakernel are two schedules of the same math."""
+def test_decode_drivers_agree(engine):
+    """The per-phase CUDA-graph driver and the two persistent kernels are three schedules of the same math."""
     pcm = read_wav_f32(synth_wav(2))
     g = golden("synth_s2_oneshot")
     out = {}
-    for mode in ("graph", "mega"):
+    for mode in ("graph", "mega", "persist"):
         engine.set_decode_mode(mode)
         out[mode], text, _ = run_stream(engine, pcm)
         check_against(g, out[mode], text)
     engine.set_decode_mode("auto")
-    assert out["graph"].tolist() == out["mega"].tolist()
+    assert out["graph"].tolist() == out["mega"].tolist() == out["persist"].tolist()
 
 
 def test_chunked_1s_tokens_match_reference(engine):

@@ -349,23 +349,30 @@ static void set_state(VbEngine *e, int pos, int token, int adapter_row, const fl
     VB_CUDA_OK(cudaStreamSynchronize(e->stream));   /* h is on the stack */
 }
 
-static int use_mega(VbEngine *e) {
+/* returns the decode driver to use: 1 graph, 2 TMA-ring persistent kernel, 3 direct-load persistent kernel */
+static int decode_driver(VbEngine *e) {
     if (e->decode_mode == 0) {
-        const char *m = getenv("VOX_CUDA_DECODE");            /* "graph" forces the per-phase CUDA-graph path */
-        e->decode_mode = (m && !strcmp(m, "graph")) ? 1 : 2;
-        if (e->decode_mode == 2 && !vb_decoder_mega_supported(e)) {
-            fprintf(stderr, "voxtral_b200: cooperative megakernel unavailable on this device, using the CUDA-graph path\n");
-            e->decode_mode = 1;
-        }
+        const char *m = getenv("VOX_CUDA_DECODE");
+        if (m && !strcmp(m, "graph")) e->decode_mode = 1;
+        else if (m && !strcmp(m, "mega")) e->decode_mode = 2;
+        else if (m && !strcmp(m, "persist")) e->decode_mode = 3;
+        else e->decode_mode = vb_decoder_persist_supported(e) ? 3 : 1;
     }
-    return e->decode_mode == 2;
+    if (e->decode_mode == 2 && !vb_decoder_mega_supported(e)) {   /* also sets the kernel's shared-memory attribute */
+        fprintf(stderr, "voxtral_b200: TMA-ring megakernel requested but unavailable on this device\n"); abort();
+    }
+    if (e->decode_mode == 3 && !vb_decoder_persist_supported(e)) {
+        fprintf(stderr, "voxtral_b200: persistent decode kernel requested but cooperative launch is unavailable\n"); abort();
+    }
+    return e->decode_mode;
 }
 
 extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps,
                                     int prev_token, int pos, int *out_tokens_host) {
     if (n_steps <= 0) return 0;
     vb_decoder_alloc(e);
-    const int mega = use_mega(e);
+    const int driver = decode_driver(e);
+    const int mega = driver >= 2;
     const int max_chunk = mega ? 2048 : e->tokens_cap;          /* bound the lifetime of one persistent launch */
     int done = 0;
     double total_ms = 0;
@@ -374,7 +381,8 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
         if (chunk > max_chunk) chunk = max_chunk;
         if (mega) {
             VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
-            vb_decoder_mega_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
+            if (driver == 2) vb_decoder_mega_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
+            else vb_decoder_persist_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             VB_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         } else {
             set_state(e, pos + done, prev_token, adapter_row + done, d_adapter);
@@ -396,7 +404,7 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
         VB_CUDA_OK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream));
         cudaError_t serr = cudaStreamSynchronize(e->stream);
         if (serr != cudaSuccess) {
-            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), mega ? "megakernel" : "graph");
+            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), driver == 1 ? "graph" : driver == 2 ? "tma-ring" : "persist");
             abort();
         }
         VB_CUDA_OK(cudaMemcpy(e->h_tokens_pinned, e->d_tokens, (size_t)st.n_out * 4, cudaMemcpyDeviceToHost));

@@ -103,7 +103,7 @@ typedef struct VbEngine {
     int *h_tokens_pinned;
     float *d_embed_in;                          /* [3072] staging for the host-pointer API */
     unsigned int *d_mega_bar;                   /* grid-barrier counter + error word of the persistent kernel */
-    int decode_mode;                            /* 0 = auto, 1 = CUDA-graph phases, 2 = persistent megakernel */
+    int decode_mode;                            /* 0 = auto, 1 = CUDA-graph phases, 2 = persistent kernel with TMA weight ring, 3 = persistent kernel, direct loads + L2 prefetch */
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
 
@@ -149,6 +149,10 @@ void vb_decoder_prefill_dev(VbEngine *e, const float *d_embeds, int n, int start
 /* vb_decode_mega.cu */
 int  vb_decoder_mega_supported(VbEngine *e);
 int  vb_decoder_mega_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
+
+/* vb_decode_persist.cu */
+int  vb_decoder_persist_supported(VbEngine *e);
+int  vb_decoder_persist_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 
 /* vb_encoder.cu */
 void vb_encoder_layers_dev(VbEngine *e, float *d_x, int new_len, int cache_len, int logical_start, int update_tail);
