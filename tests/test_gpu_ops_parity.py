@@ -88,7 +88,10 @@ def test_linear_bf16(vb, ref, M, K, N, bias):
     bp = P(b) if bias else None
     vb.lib().vox_linear_bf16(P(ya), P(x), W.ctypes.data_as(u16p), bp, M, K, N)
     ref.L.vox_linear_bf16(P(yb), P(x), W.ctypes.data_as(u16p), bp, M, K, N)
-    close(ya, yb, 1e-5)
+    # M == 1 runs the f32 FMA GEMV (decode path): 1e-5.  M > 1 runs on the tensor cores: products are exact (bf16 weight x
+    # bf16 activation planes) but the tcgen05 accumulator does not round like an IEEE FMA chain -> ~1e-5 of the row scale
+    # (measured 1.1e-5 at K=3072, identical with 2 or 3 planes), so 3e-5.
+    close(ya, yb, 1e-5 if M == 1 else 3e-5)
 
 
 def test_linear_f32_and_matmul(vb, ref):
@@ -120,6 +123,8 @@ def test_softmax(vb, ref):
     (1, 300, 32, 8, 128, 8192, 299),        # decode step, GQA
     (38, 38, 32, 8, 128, 8192, 0),          # prefill
     (20, 820, 32, 32, 64, 750, 800),        # encoder chunk against a full window (mask on both sides)
+    (150, 900, 32, 32, 64, 750, 750),       # several 64-query tiles, ragged last tile, window start inside a key tile
+    (70, 70, 32, 32, 64, 750, 0),           # stream start: keys < window
     (9, 9, 4, 2, 32, 3, 0),                 # tiny window
 ])
 def test_causal_attention(vb, ref, seq_q, seq_k, H, Hkv, hd, win, qoff):

@@ -124,9 +124,23 @@ static void gemm_dispatch(VbEngine *e, const float *A, int lda, const WT *W, con
     vb_launch_count(e, 1);
 }
 
+/* M>1 bf16-weight GEMMs go to the tensor cores (vb_gemm_tc.cu) whenever the shape tiles (N%128, K%64 -- every
+ * linear of the model does); VOX_CUDA_GEMM=simt forces the f32 CUDA-core kernel (validation). */
+void vb_gemm_tc(VbEngine *e, const float *A, int lda, const uint16_t *W, const float *bias, float *C, int ldc,
+                int M, int N, int K, int epi);
+int vb_gemm_tc_usable(int M, int N, int K);
+static int gemm_use_tc(void) {
+    static int mode = -1;
+    if (mode < 0) { const char *s = getenv("VOX_CUDA_GEMM"); mode = (s && !strcmp(s, "simt")) ? 0 : 1; }
+    return mode;
+}
 void vb_gemm_bf16w(VbEngine *e, const float *A, int lda, const uint16_t *W, const float *bias,
                    float *C, int ldc, int M, int N, int K, int epi) {
-    gemm_dispatch<uint16_t>(e, A, lda, W, bias, C, ldc, M, N, K, epi);
+    if (M <= 0 || N <= 0) return;
+    if (gemm_use_tc() && M >= 8 && vb_gemm_tc_usable(M, N, K) && (lda % 4) == 0 && (ldc % 4) == 0)
+        vb_gemm_tc(e, A, lda, W, bias, C, ldc, M, N, K, epi);
+    else
+        gemm_dispatch<uint16_t>(e, A, lda, W, bias, C, ldc, M, N, K, epi);
 }
 void vb_gemm_f32w(VbEngine *e, const float *A, int lda, const float *W, const float *bias,
                   float *C, int ldc, int M, int N, int K, int epi) {
@@ -272,10 +286,150 @@ k_attn_warp(float *__restrict__ out, int ldo, const float *__restrict__ Q, int l
     for (int t = 0; t < EPL; t++) out[(size_t)i * ldo + h * hd + lane * EPL + t] = o[t] * inv;
 }
 
+/* Tiled flash attention for the encoder shape (head_dim 64, MHA): one CTA = 64 queries of one head, K/V streamed in
+ * 64-key tiles through shared memory, S = QK^T and O += PV as 4x4 register blocks, online softmax per row.
+ * Same masking as k_attn_warp (keys [max(0,g-W+1), min(g,seq_k-1)], g = q_offset+i); exact f32 arithmetic. */
+#define AT_BQ 64
+#define AT_BK 64
+#define AT_HD 64
+#define AT_LD 68                      /* padded leading dimension (floats) of the transposed tiles */
+__global__ void __launch_bounds__(256, 2)
+k_attn_tile64(float *__restrict__ out, int ldo, const float *__restrict__ Q, int ldq,
+              const float *__restrict__ K, const float *__restrict__ V, int ldkv,
+              int seq_q, int seq_k, float scale, int window, int q_offset) {
+    extern __shared__ float at_smem[];
+    float *Qt = at_smem;                         /* [d][q]  */
+    float *Kt = Qt + AT_HD * AT_LD;              /* [d][k]  */
+    float *Vs = Kt + AT_HD * AT_LD;              /* [k][d]  */
+    float *Pt = Vs + AT_BK * AT_LD;              /* [k][q]  */
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int h = blockIdx.y, q0 = blockIdx.x * AT_BQ;
+    const int hoff = h * AT_HD;
+
+    for (int i = tid; i < AT_BQ * (AT_HD / 4); i += 256) {          /* Q tile, transposed, pre-scaled */
+        int r = i % AT_BQ, c4 = (i / AT_BQ) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + r < seq_q) v = *reinterpret_cast<const float4 *>(Q + (size_t)(q0 + r) * ldq + hoff + c4);
+        Qt[(c4 + 0) * AT_LD + r] = v.x * scale; Qt[(c4 + 1) * AT_LD + r] = v.y * scale;
+        Qt[(c4 + 2) * AT_LD + r] = v.z * scale; Qt[(c4 + 3) * AT_LD + r] = v.w * scale;
+    }
+    float o[4][4], m[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { m[i] = -1e30f; l[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[i][j] = 0.f; }
+
+    const int g_first = q_offset + q0, g_last = q_offset + min(q0 + AT_BQ, seq_q) - 1;
+    int k_lo = 0;
+    if (window > 0 && g_first - window + 1 > 0) k_lo = g_first - window + 1;
+    int k_hi = min(g_last + 1, seq_k);                              /* exclusive */
+    k_lo = (k_lo / AT_BK) * AT_BK;
+
+    for (int kt = k_lo; kt < k_hi; kt += AT_BK) {
+        __syncthreads();                                            /* previous tile fully consumed (also covers Qt) */
+        for (int i = tid; i < AT_BK * (AT_HD / 4); i += 256) {
+            {   /* K: lanes walk the key index so the transposed shared-memory stores are conflict free
+                 * (the strided global reads are L2 hits: every K row is used by ~13 query tiles) */
+                int r = i % AT_BK, c4 = (i / AT_BK) * 4;
+                float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kt + r < seq_k) kv = *reinterpret_cast<const float4 *>(K + (size_t)(kt + r) * ldkv + hoff + c4);
+                Kt[(c4 + 0) * AT_LD + r] = kv.x; Kt[(c4 + 1) * AT_LD + r] = kv.y;
+                Kt[(c4 + 2) * AT_LD + r] = kv.z; Kt[(c4 + 3) * AT_LD + r] = kv.w;
+            }
+            {   /* V: row-major, coalesced */
+                int r = i / (AT_HD / 4), c4 = (i % (AT_HD / 4)) * 4;
+                float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kt + r < seq_k) vv = *reinterpret_cast<const float4 *>(V + (size_t)(kt + r) * ldkv + hoff + c4);
+                *reinterpret_cast<float4 *>(Vs + r * AT_LD + c4) = vv;
+            }
+        }
+        __syncthreads();
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) s[i][j] = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < AT_HD; d++) {
+            const float4 a = *reinterpret_cast<const float4 *>(Qt + d * AT_LD + ty * 4);
+            const float4 b = *reinterpret_cast<const float4 *>(Kt + d * AT_LD + tx * 4);
+            const float av[4] = { a.x, a.y, a.z, a.w }, bv[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) s[i][j] = fmaf(av[i], bv[j], s[i][j]);
+        }
+        /* mask + online softmax (rows are shared by the 16 threads with the same ty = one half-warp) */
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int g = q_offset + q0 + ty * 4 + i;
+            int lo = 0;
+            if (window > 0 && g - window + 1 > 0) lo = g - window + 1;
+            float mx = -1e30f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int kj = kt + tx * 4 + j;
+                const bool ok = kj >= lo && kj <= g && kj < seq_k;
+                s[i][j] = ok ? s[i][j] : -1e30f;
+                mx = fmaxf(mx, s[i][j]);
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float mn = fmaxf(m[i], mx);
+            const float corr = expf(m[i] - mn);
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float p = s[i][j] > -1e29f ? expf(s[i][j] - mn) : 0.f;
+                s[i][j] = p; rs += p;
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+            l[i] = l[i] * corr + rs;
+            m[i] = mn;
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[i][j] *= corr;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            *reinterpret_cast<float4 *>(Pt + (tx * 4 + j) * AT_LD + ty * 4) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < AT_BK; k++) {
+            const float4 a = *reinterpret_cast<const float4 *>(Pt + k * AT_LD + ty * 4);
+            const float4 b = *reinterpret_cast<const float4 *>(Vs + k * AT_LD + tx * 4);
+            const float av[4] = { a.x, a.y, a.z, a.w }, bv[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) o[i][j] = fmaf(av[i], bv[j], o[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = q0 + ty * 4 + i;
+        if (r < seq_q) {
+            const float inv = l[i] > 0.f ? 1.0f / l[i] : 0.f;
+            *reinterpret_cast<float4 *>(out + (size_t)r * ldo + hoff + tx * 4) =
+                make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+        }
+    }
+}
+
 void vb_attention_rows(VbEngine *e, float *out, int ldo, const float *Q, int ldq, const float *K,
                        const float *V, int ldkv, int seq_q, int seq_k, int n_heads, int n_kv_heads,
                        int head_dim, float scale, int window, int q_offset) {
     if (seq_q <= 0) return;
+    if (head_dim == AT_HD && n_heads == n_kv_heads && seq_q >= 16 && (ldq % 4) == 0 && (ldkv % 4) == 0 && (ldo % 4) == 0) {
+        static int attr_done = 0;
+        const int smem = 4 * AT_HD * AT_LD * (int)sizeof(float);
+        if (!attr_done) { VB_CUDA_OK(cudaFuncSetAttribute(k_attn_tile64, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_done = 1; }
+        dim3 grid((seq_q + AT_BQ - 1) / AT_BQ, n_heads);
+        k_attn_tile64<<<grid, 256, smem, e->stream>>>(out, ldo, Q, ldq, K, V, ldkv, seq_q, seq_k, scale, window, q_offset);
+        VB_CUDA_OK(cudaGetLastError());
+        vb_launch_count(e, 1);
+        return;
+    }
     long long warps = (long long)seq_q * n_heads;
     int blocks = (int)((warps * 32 + 255) / 256);
 #define ATT_CASE(E) case E: k_attn_warp<E><<<blocks, 256, 0, e->stream>>>(out, ldo, Q, ldq, K, V, ldkv, seq_q, seq_k, \
