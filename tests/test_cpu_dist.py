@@ -1,0 +1,54 @@
+"""world_size-2 gloo run of the N>1 host logic (stream assignment + the max-over-ranks timing reduction that
+bench.py uses under NCCL).  CPU only."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import vbload
+    multi = vbload.load_submodule("multi")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = multi.assign_streams(5, world, rank)
+    # rank 0 "takes" 1.5 s for 3 streams of 10 s audio, rank 1 takes 2.5 s for 2 streams
+    elapsed = 1500.0 if rank == 0 else 2500.0
+    agg = multi.aggregate_rtf(10.0 * len(mine), elapsed, dist)
+    mx = multi.reduce_max([elapsed, float(rank)], dist)
+    out[rank] = (mine, agg, mx)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo():
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    (s0, a0, m0), (s1, a1, m1) = out[0], out[1]
+    assert s0 == [0, 1, 2] and s1 == [3, 4]                      # contiguous, balanced, disjoint, complete
+    assert a0 == a1                                              # every rank sees the same aggregate
+    assert a0["audio_s"] == 50.0 and a0["elapsed_ms"] == 2500.0 and abs(a0["rtf"] - 20.0) < 1e-12
+    assert m0 == m1 == [2500.0, 1.0]
+
+
+def test_assign_streams_properties():
+    import vbload
+    multi = vbload.load_submodule("multi")
+    for n in (0, 1, 7, 8, 9, 64):
+        for w in (1, 2, 4, 8):
+            parts = [multi.assign_streams(n, w, r) for r in range(w)]
+            flat = [i for p in parts for i in p]
+            assert flat == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert multi.reduce_max([1.0, 2.0]) == [1.0, 2.0]            # no process group: identity
