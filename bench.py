@@ -201,6 +201,7 @@ def main():
     model, pcm = ensure_inputs(args.seconds)
     import vbload
     vb = vbload.load()
+    multi = vbload.load_submodule("multi")
     eng = vb.Engine(model)
     info0 = eng.info()
     d_pcm = eng.to_device(pcm)
@@ -227,13 +228,14 @@ def main():
         wall = time.perf_counter() - t0
         if dist is not None:
             import torch
-            t = torch.tensor([dev_ms, wall * 1e3], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dev_ms, wall = float(t[0]), float(t[1]) / 1e3
+            dev_ms, wall_ms = multi.reduce_max([dev_ms, wall * 1e3], dist, torch.device("cuda", local))
+            wall = wall_ms / 1e3
         barrier()
         return dev_ms, wall, ids, c
 
-    for _ in range(max(args.warmup, 3)):
+    profiling = os.environ.get("VOX_BENCH_PROFILE") == "1"      # ncu runs: fewer warm-ups, no CPU leg (never a bench value)
+    n_warm = args.warmup if profiling else max(args.warmup, 3)
+    for _ in range(n_warm):
         ids, counts = one_pass(True)
     sampler = ClockSampler(local); sampler.start()
     i_before = eng.info()
@@ -256,10 +258,10 @@ def main():
     peak, peak_src = peaks()
 
     if rank == 0:
-        cpu = reference_sample(model, args.seconds) if world == 1 else None
+        cpu = reference_sample(model, args.seconds) if (world == 1 and not profiling) else None
         line = {
             "metric": "real-time factor (audio-s/wall-s)", "value": value, "unit": "x real-time", "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "steps": args.steps, "warmup": n_warm, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 activations x bf16 weights, f32 accumulate", "data": "synthetic",
             "config": {"workload": workload, "streams": world, "mel_frames": counts["mel_frames"],
