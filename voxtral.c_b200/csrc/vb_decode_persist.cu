@@ -5,11 +5,10 @@
  * separated by grid barriers; the token feedback stays on the device) but the weights are NOT staged through
  * shared memory: every thread streams its own k-columns with 128-bit ld.global.nc.L1::no_allocate loads,
  * 16 rows in flight per thread (the GEMV core that reaches 99% of the measured HBM peak inside the logits
- * phase, profiles/).  What a phase boundary costs -- drain, barrier latency, skew between CTAs, the activation
- * reload -- is attacked by software-pipelining the weight loads ACROSS the boundary: the first batch of the next
- * phase (16 rows, 98 KB per SM) is issued into registers before the CTA enters the grid barrier, so HBM keeps
- * streaming while the SMs synchronise.  (An optional cp.async.bulk.prefetch.L2 look-ahead exists but is off:
- * measured, it only moves time from the phases into the barriers.)
+ * phase, profiles/r01_launches_graph.md).  What a phase boundary costs -- barrier latency, skew between
+ * CTAs, the activation reload -- is hidden differently: just before a CTA enters a grid barrier it issues ONE
+ * cp.async.bulk.prefetch.L2 for the next `l2_ahead` bytes of its own slab schedule.  HBM therefore keeps
+ * streaming while the SMs wait, and the first rows of the next phase are L2 hits.
  *
  * Reference semantics: voxtral_decoder.c:586-706 per step, voxtral.c:1056-1093 for the loop.
  */
@@ -18,50 +17,34 @@
 
 #define PK_L2_AHEAD 0   /* measured: L2 prefetch only moves time from the phases into the barriers (profiles/r01_decode_persist.md) */
 
-/* One batch of weight loads: RB rows x CPT 16-byte chunks per thread (RB = 16 for CPT 1, 4 for CPT 3), rows
- * [r_off, r_off+RB) of the CTA's slab; rows past the slab are predicated off. */
-template <int CPT>
-__device__ __forceinline__ void issue_batch(uint4 (&w)[16], const Phase &f, int K, int NT, int r_off) {
-    constexpr int RB = (CPT == 1) ? 16 : 4;
-    const int t = threadIdx.x;
-    const uint16_t *wt = f.W + (size_t)t * 8;
-#pragma unroll
-    for (int r = 0; r < RB; r++)
-#pragma unroll
-        for (int c = 0; c < CPT; c++) {
-            if (t < NT && r_off + r < f.nrows)
-                w[r * CPT + c] = ldg_stream16(wt + (size_t)(f.row0 + r_off + r) * K + (size_t)c * NT * 8);
-            else w[r * CPT + c] = make_uint4(0u, 0u, 0u, 0u);
-        }
-}
-
-/* y[row] = W[row,:] . x for the CTA's rows, software-pipelined ACROSS phase boundaries: on entry `w` already holds the
- * phase's first batch (issued before the preceding barrier); after the FMAs of every batch the next batch is issued
- * into the same registers -- and after the last batch, the first batch of the NEXT phase (issue_next), so that its
- * HBM latency overlaps this phase's reduction, the grid barrier, the activation reload and the RMSNorm. */
-template <int CPT, typename Epi, typename IssueNext>
-__device__ __forceinline__ void gemv_pipe(const Phase &f, int K, int NT, const float (&xr)[CPT * 8], uint4 (&w)[16],
-                                          float (*red)[16][MK_GROUP], int &redbuf, Epi epi, IssueNext issue_next) {
-    constexpr int RB = (CPT == 1) ? 16 : 4;
+/* y[row] = W[row,:] . x for the CTA's rows, 16 rows of 128-bit loads in flight per thread. */
+template <int CPT, typename Epi>
+__device__ __forceinline__ void gemv_stream(const Phase &f, int K, int NT, const float (&xr)[CPT * 8],
+                                            float (*red)[16][MK_GROUP], int &redbuf, Epi epi) {
+    constexpr int R = (CPT == 1) ? 16 : 4;             /* rows per batch of loads (register budget) */
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool active = t < NT;
+    const uint16_t *wt = f.W + (size_t)t * 8;
     for (int g0 = 0; g0 < f.nrows; g0 += MK_GROUP) {
         const int gr = min(MK_GROUP, f.nrows - g0);
         float acc[MK_GROUP];
 #pragma unroll
-        for (int i = 0; i < MK_GROUP; i++) acc[i] = 0.f;
+        for (int rb = 0; rb < MK_GROUP; rb += R) {
+            uint4 w[R][CPT];
 #pragma unroll
-        for (int rb = 0; rb < MK_GROUP; rb += RB) {
-            if (g0 + rb < f.nrows) {
+            for (int r = 0; r < R; r++)
 #pragma unroll
-                for (int r = 0; r < RB; r++) {
-                    float sacc = 0.f;
-#pragma unroll
-                    for (int c = 0; c < CPT; c++) sacc = dot8(w[r * CPT + c], &xr[c * 8], sacc);
-                    acc[rb + r] = sacc;
+                for (int c = 0; c < CPT; c++) {
+                    if (active && rb + r < gr)
+                        w[r][c] = ldg_stream16(wt + (size_t)(f.row0 + g0 + rb + r) * K + (size_t)c * NT * 8);
+                    else w[r][c] = make_uint4(0u, 0u, 0u, 0u);
                 }
-                const int next_r = g0 + rb + RB;
-                if (next_r < f.nrows) issue_batch<CPT>(w, f, K, NT, next_r);
-                else issue_next(w);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < CPT; c++) s = dot8(w[r][c], &xr[c * 8], s);
+                acc[rb + r] = s;
             }
         }
         float tot = warp_transpose_reduce<MK_GROUP>(acc, lane);
@@ -137,8 +120,6 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
     int n_done = 0, eos = 0, prof_n = 0;
     PrefetchCursor pc;
     pc.start();
-    uint4 w[16];                               /* the weight batch in flight; survives phase boundaries */
-    {   Phase f0 = phase_of(p, 0, 0); issue_batch<1>(w, f0, VOX_DEC_DIM, VOX_DEC_DIM / 8, 0); }
 
     for (int step = 0; step < a.n_steps; step++) {
         const float *arow_p = adapter + (size_t)arow * VOX_DEC_DIM;
@@ -172,7 +153,7 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                 float *vdst = p.kv_v + ((size_t)layer * VB_KV_SLOTS + slot) * VB_DEC_KV;
                 const float *inv_freq = p.inv_freq;
                 float *q = p.q;
-                gemv_pipe<1>(f, VOX_DEC_DIM, NT, xr, w, red, redbuf, [&](int row, float v, int, bool valid) {
+                gemv_stream<1>(f, VOX_DEC_DIM, NT, xr, red, redbuf, [&](int row, float v, int, bool valid) {
                     float other = __shfl_xor_sync(0xffffffffu, v, 1);
                     if (!valid) return;
                     if (row < VB_DEC_Q + VB_DEC_KV) {
@@ -182,7 +163,7 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                         float y = (row & 1) ? (other * sn + v * cs) : (v * cs - other * sn);
                         if (row < VB_DEC_Q) q[row] = y; else kdst[row - VB_DEC_Q] = y;
                     } else vdst[row - VB_DEC_Q - VB_DEC_KV] = v;
-                }, [&](uint4 (&)[16]) {});               /* the attention phase follows: nothing to prefetch into registers */
+                });
             }
             PROF(1);
             if (tid == 0) pc.after_phase(p, a.n_steps, step, layer, 0, a.l2_ahead);
@@ -191,7 +172,6 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
             mega_attention(p, layer, pos, &is_last, att_scr, a.bar + 16);
             PROF(3);
             if (tid == 0) pc.extend(p, a.n_steps, 2 * a.l2_ahead);      /* the attention phase streamed no weights */
-            {   Phase fw = phase_of(p, layer, 1); issue_batch<1>(w, fw, VB_DEC_Q, VB_DEC_Q / 8, 0); }   /* wo's first rows fly during the barrier */
             grid_barrier(a.bar, gen, a.err);
             PROF(4);
             {   /* ---- wo + residual ---- */
@@ -200,9 +180,9 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                 load_x_cols_cg<1>(xr, p.attn_out, NT);
                 Phase f = phase_of(p, layer, 1);
                 float *x = p.x;
-                gemv_pipe<1>(f, VB_DEC_Q, NT, xr, w, red, redbuf, [&](int row, float v, int, bool valid) {
+                gemv_stream<1>(f, VB_DEC_Q, NT, xr, red, redbuf, [&](int row, float v, int, bool valid) {
                     if (valid) x[row] = __ldcg(x + row) + v;
-                }, [&](uint4 (&wn)[16]) { Phase fn = phase_of(p, layer, 2); issue_batch<1>(wn, fn, VOX_DEC_DIM, VOX_DEC_DIM / 8, 0); });
+                });
             }
             PROF(5);
             if (tid == 0) pc.after_phase(p, a.n_steps, step, layer, 1, a.l2_ahead);
@@ -215,10 +195,10 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                 rmsnorm_cols_cons<1>(xr, p.ffn_norm[layer], p.ada + (size_t)layer * VOX_DEC_DIM, NT, VOX_DEC_DIM, sred);
                 Phase f = phase_of(p, layer, 2);
                 float *gate = p.gate;
-                gemv_pipe<1>(f, VOX_DEC_DIM, NT, xr, w, red, redbuf, [&](int row, float v, int, bool valid) {
+                gemv_stream<1>(f, VOX_DEC_DIM, NT, xr, red, redbuf, [&](int row, float v, int, bool valid) {
                     float other = __shfl_xor_sync(0xffffffffu, v, 1);
                     if (valid && !(row & 1)) gate[row >> 1] = vb_silu(v) * other;
-                }, [&](uint4 (&wn)[16]) { Phase fn = phase_of(p, layer, 3); issue_batch<3>(wn, fn, VOX_DEC_HIDDEN, VOX_DEC_HIDDEN / 8 / 3, 0); });
+                });
             }
             PROF(7);
             if (tid == 0) pc.after_phase(p, a.n_steps, step, layer, 2, a.l2_ahead);
@@ -230,11 +210,8 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                 load_x_cols_cg<3>(xr, p.gate, NT);
                 Phase f = phase_of(p, layer, 3);
                 float *x = p.x;
-                gemv_pipe<3>(f, VOX_DEC_HIDDEN, NT, xr, w, red, redbuf, [&](int row, float v, int, bool valid) {
+                gemv_stream<3>(f, VOX_DEC_HIDDEN, NT, xr, red, redbuf, [&](int row, float v, int, bool valid) {
                     if (valid) x[row] = __ldcg(x + row) + v;
-                }, [&](uint4 (&wn)[16]) {
-                    Phase fn = layer + 1 < VOX_DEC_LAYERS ? phase_of(p, layer + 1, 0) : phase_of(p, 0, 4);
-                    issue_batch<1>(wn, fn, VOX_DEC_DIM, VOX_DEC_DIM / 8, 0);
                 });
             }
             PROF(9);
@@ -250,13 +227,11 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
             Phase f = phase_of(p, 0, 4);
             float *logits = p.logits;
             unsigned long long best = 0ull;
-            gemv_pipe<1>(f, VOX_DEC_DIM, NT, xr, w, red, redbuf, [&](int row, float v, int, bool valid) {
+            gemv_stream<1>(f, VOX_DEC_DIM, NT, xr, red, redbuf, [&](int row, float v, int, bool valid) {
                 if (!valid) return;
                 logits[row] = v;
                 unsigned long long c = pack_cand(v, row);
                 if (c > best) best = c;
-            }, [&](uint4 (&wn)[16]) {
-                if (step + 1 < a.n_steps) { Phase fn = phase_of(p, 0, 0); issue_batch<1>(wn, fn, VOX_DEC_DIM, VOX_DEC_DIM / 8, 0); }
             });
             if (tid < 32) {
 #pragma unroll
