@@ -343,6 +343,23 @@ int vox_cuda_decoder_prefill(vox_ctx_t *ctx, const float *d_embeds, int n);
 int vox_cuda_decoder_steps(vox_ctx_t *ctx, const float *d_adapter, int first_pos,
                            int n_steps, int prev_token, int *out_tokens);
 
+/* Building blocks for the sequence-sharded encoder (BASELINE.json configs[4]).  A layer is split in two
+ * so that ranks holding contiguous position ranges can exchange the 750-row K/V halo between the halves:
+ *   vox_cuda_encoder_layer_qkv : RMSNorm -> q|k|v (+bias) -> RoPE(pos0+i); K,V rows go to d_k/d_v[row_off + i] ([rows,2048] f32)
+ *   vox_cuda_encoder_layer_rest: attention over d_k/d_v rows [0, q_off+M) with query i at row q_off+i, then wo, FFN, residuals
+ * x is [M,1280] f32 on the device and is updated in place.  All work is enqueued on the ctx's stream; vox_cuda_sync waits for it. */
+int  vox_cuda_mel_conv_stem(vox_ctx_t *ctx, const float *d_mel, int mel_frames, float *d_out);   /* [F,128] -> [ceil(F/2),1280] */
+int  vox_cuda_encoder_layer_qkv(vox_ctx_t *ctx, int layer, const float *d_x, int M, int pos0, float *d_k, float *d_v, int row_off);
+int  vox_cuda_encoder_layer_rest(vox_ctx_t *ctx, int layer, float *d_x, int M, const float *d_k, const float *d_v, int q_off);
+int  vox_cuda_encoder_final_norm(vox_ctx_t *ctx, float *d_x, int M);
+int  vox_cuda_adapter(vox_ctx_t *ctx, const float *d_enc, int enc_len, float *d_out);           /* -> enc_len/4 rows of 3072 */
+void vox_cuda_sync(vox_ctx_t *ctx);
+/* device view of an incremental mel context's frames ([n_frames,128] f32) and the prompt-embedding builder
+ * (out[i] = adapter[i] + tok_embed(i == 0 ? BOS : STREAMING_PAD), voxtral.c:990-999) */
+float *vox_cuda_mel_device_frames(vox_mel_ctx_t *mel, int *n_frames);
+int  vox_cuda_mel_feed_zeros(vox_mel_ctx_t *mel, int n);
+int  vox_cuda_build_prompt(vox_ctx_t *ctx, float *d_out, const float *d_adapter, int n);
+
 /* Introspection for tests and bench.py */
 typedef struct {
     int    device;               /* CUDA ordinal this ctx lives on */

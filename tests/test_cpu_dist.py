@@ -52,3 +52,21 @@ def test_assign_streams_properties():
             assert flat == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     assert multi.reduce_max([1.0, 2.0]) == [1.0, 2.0]            # no process group: identity
+
+
+def test_shard_plan_properties():
+    """Host logic of the sequence-sharded encoder: contiguous 4-aligned ranges, complete, balanced; halo sizes."""
+    import vbload
+    sh = vbload.load_submodule("sharded")
+    for P in (748, 1696, 30196, 180196, 180199):
+        for w in (1, 2, 4, 8):
+            plan = sh.plan_shards(P, w)
+            assert plan[0][0] == 0 and plan[-1][1] == 4 * (P // 4)
+            for (a, b), (c, d) in zip(plan, plan[1:]):
+                assert b == c
+            assert all(a % 4 == 0 and b % 4 == 0 for a, b in plan)
+            sizes = [b - a for a, b in plan]
+            assert max(sizes) - min(sizes) <= 4
+    assert sh.halo_rows(0) == 0 and sh.halo_rows(300) == 300 and sh.halo_rows(22524) == 750
+    # 1-hour config: 8 ranks x ~22.5k positions, each far larger than the 750-row window
+    assert min(b - a for a, b in sh.plan_shards(180196, 8)) >= 22520

@@ -93,6 +93,14 @@ def lib():
         "vox_tokenizer_decode": (C.c_char_p, [vp, i]),
         "vox_cuda_get_info": (i, [vp, C.POINTER(CudaInfo)]), "vox_cuda_version": (C.c_char_p, []),
         "vox_cuda_reset_caches": (None, [vp]), "vox_cuda_set_decode_mode": (None, [vp, i]),
+        "vox_cuda_mel_conv_stem": (i, [vp, vp, i, vp]),
+        "vox_cuda_encoder_layer_qkv": (i, [vp, i, vp, i, i, vp, vp, i]),
+        "vox_cuda_encoder_layer_rest": (i, [vp, i, vp, i, vp, vp, i]),
+        "vox_cuda_encoder_final_norm": (i, [vp, vp, i]), "vox_cuda_adapter": (i, [vp, vp, i, vp]),
+        "vox_cuda_sync": (None, [vp]), "vox_cuda_mel_device_frames": (vp, [vp, c_int_p]),
+        "vox_cuda_mel_feed_zeros": (i, [vp, i]), "vox_cuda_build_prompt": (i, [vp, vp, vp, i]),
+        "vox_cuda_decoder_prefill": (i, [vp, vp, i]), "vox_cuda_decoder_steps": (i, [vp, vp, i, i, i, c_int_p]),
+        "vox_cuda_encoder_step": (i, [vp, vp, i]),
         "vox_cuda_stream_feed_device": (i, [vp, vp, i]),
         "vox_cuda_malloc": (vp, [vp, C.c_size_t]), "vox_cuda_free": (None, [vp, vp]),
         "vox_cuda_memcpy_h2d": (i, [vp, vp, vp, C.c_size_t]), "vox_cuda_memcpy_d2h": (i, [vp, vp, vp, C.c_size_t]),

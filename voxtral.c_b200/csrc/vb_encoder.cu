@@ -31,40 +31,57 @@ static void enc_alloc_tail(VbEngine *e) {
     e->kv_bytes += 2 * bytes;
 }
 
+/* One encoder layer in two halves, so that a sequence-sharded run can exchange K/V halos in between
+ * (SURVEY.md section 8e): layer-l K/V of a position depend only on that position's layer-(l-1) state, so ranks that
+ * each hold a contiguous position range proceed in lock-step and rank r only needs rank r-1's last 750 K/V rows.
+ *   first half : RMSNorm -> [wq|wk|wv] GEMM (+bias) -> RoPE(pos0+i) -> K,V rows written at kb/vb[row_off + i]
+ *   second half: window-750 attention over kb/vb rows [0, q_off + M) with q_offset = q_off -> wo(+bias)+res -> RMSNorm ->
+ *                SwiGLU -> w2(+bias)+res.  x: [M,1280] updated in place. */
+extern "C" void vb_enc_layer_qkv_dev(VbEngine *e, int l, const float *x, int M, int pos0, float *kb, float *vb, int row_off) {
+    const VbEncLayerDev &w = e->enc[l];
+    float *xn  = vb_ws(e, 1, (size_t)M * ENC_DIM * 4);
+    float *qkv = vb_ws(e, 2, (size_t)M * VB_ENC_QKV * 4);
+    vb_rmsnorm_rows(e, xn, x, w.attn_norm, nullptr, M, ENC_DIM, VOX_ENC_NORM_EPS);
+    vb_gemm_bf16w(e, xn, ENC_DIM, w.wqkv, w.bqkv, qkv, VB_ENC_QKV, M, VB_ENC_QKV, ENC_DIM, VB_EPI_STORE);
+    vb_rope_split(e, qkv, VB_ENC_QKV, M, VOX_ENC_HEADS, VOX_ENC_KV_HEADS, VOX_ENC_HEAD_DIM,
+                  e->d_enc_inv_freq, pos0, kb, vb, row_off, -1);
+}
+
+extern "C" void vb_enc_layer_rest_dev(VbEngine *e, int l, float *x, int M, const float *kb, const float *vb, int q_off) {
+    const VbEncLayerDev &w = e->enc[l];
+    float *xn  = vb_ws(e, 1, (size_t)M * ENC_DIM * 4);
+    float *qkv = vb_ws(e, 2, (size_t)M * VB_ENC_QKV * 4);           /* q part written by the first half */
+    float *att = vb_ws(e, 3, (size_t)M * VB_ENC_ATT * 4);
+    float *g   = vb_ws(e, 4, (size_t)M * ENC_HID * 4);
+    const float scale = 1.0f / sqrtf((float)VOX_ENC_HEAD_DIM);
+    vb_attention_rows(e, att, VB_ENC_ATT, qkv, VB_ENC_QKV, kb, vb, VB_ENC_ATT, M, q_off + M,
+                      VOX_ENC_HEADS, VOX_ENC_KV_HEADS, VOX_ENC_HEAD_DIM, scale, ENC_WIN, q_off);
+    vb_gemm_bf16w(e, att, VB_ENC_ATT, w.wo, w.bo, x, ENC_DIM, M, ENC_DIM, VB_ENC_ATT, VB_EPI_RESIDUAL);
+    vb_rmsnorm_rows(e, xn, x, w.ffn_norm, nullptr, M, ENC_DIM, VOX_ENC_NORM_EPS);
+    vb_gemm_bf16w(e, xn, ENC_DIM, w.w13, nullptr, g, ENC_HID, M, 2 * ENC_HID, ENC_DIM, VB_EPI_SWIGLU);
+    vb_gemm_bf16w(e, g, ENC_HID, w.w2, w.b2, x, ENC_DIM, M, ENC_DIM, ENC_HID, VB_EPI_RESIDUAL);
+}
+
 /* x: [new_len,1280] device, updated in place to the encoder output (final norm applied).
  * cache_len: rows of valid tail (<=750) BEFORE this call; logical_start: RoPE position of x[0]. */
 extern "C" void vb_encoder_layers_dev(VbEngine *e, float *x, int M, int cache_len, int logical_start, int update_tail) {
     if (M <= 0) return;
     enc_alloc_tail(e);
     const int total = cache_len + M;
-    float *xn  = vb_ws(e, 1, (size_t)M * ENC_DIM * 4);
-    float *qkv = vb_ws(e, 2, (size_t)M * VB_ENC_QKV * 4);
-    float *att = vb_ws(e, 3, (size_t)M * VB_ENC_ATT * 4);
-    float *g   = vb_ws(e, 4, (size_t)M * ENC_HID * 4);
     float *kb  = vb_ws(e, 5, (size_t)total * VB_ENC_ATT * 4);
     float *vb  = vb_ws(e, 6, (size_t)total * VB_ENC_ATT * 4);
-    const float scale = 1.0f / sqrtf((float)VOX_ENC_HEAD_DIM);
     const size_t row = (size_t)VB_ENC_ATT * sizeof(float);
     const int keep = total < ENC_WIN ? total : ENC_WIN;
 
     for (int l = 0; l < VOX_ENC_LAYERS; l++) {
-        const VbEncLayerDev &w = e->enc[l];
         float *tk = e->d_enc_tail_k + (size_t)l * ENC_WIN * VB_ENC_ATT;
         float *tv = e->d_enc_tail_v + (size_t)l * ENC_WIN * VB_ENC_ATT;
         if (cache_len > 0) {
             VB_CUDA_OK(cudaMemcpyAsync(kb, tk, cache_len * row, cudaMemcpyDeviceToDevice, e->stream));
             VB_CUDA_OK(cudaMemcpyAsync(vb, tv, cache_len * row, cudaMemcpyDeviceToDevice, e->stream));
         }
-        vb_rmsnorm_rows(e, xn, x, w.attn_norm, nullptr, M, ENC_DIM, VOX_ENC_NORM_EPS);
-        vb_gemm_bf16w(e, xn, ENC_DIM, w.wqkv, w.bqkv, qkv, VB_ENC_QKV, M, VB_ENC_QKV, ENC_DIM, VB_EPI_STORE);
-        vb_rope_split(e, qkv, VB_ENC_QKV, M, VOX_ENC_HEADS, VOX_ENC_KV_HEADS, VOX_ENC_HEAD_DIM,
-                      e->d_enc_inv_freq, logical_start, kb, vb, cache_len, -1);
-        vb_attention_rows(e, att, VB_ENC_ATT, qkv, VB_ENC_QKV, kb, vb, VB_ENC_ATT, M, total,
-                          VOX_ENC_HEADS, VOX_ENC_KV_HEADS, VOX_ENC_HEAD_DIM, scale, ENC_WIN, cache_len);
-        vb_gemm_bf16w(e, att, VB_ENC_ATT, w.wo, w.bo, x, ENC_DIM, M, ENC_DIM, VB_ENC_ATT, VB_EPI_RESIDUAL);
-        vb_rmsnorm_rows(e, xn, x, w.ffn_norm, nullptr, M, ENC_DIM, VOX_ENC_NORM_EPS);
-        vb_gemm_bf16w(e, xn, ENC_DIM, w.w13, nullptr, g, ENC_HID, M, 2 * ENC_HID, ENC_DIM, VB_EPI_SWIGLU);
-        vb_gemm_bf16w(e, g, ENC_HID, w.w2, w.b2, x, ENC_DIM, M, ENC_DIM, ENC_HID, VB_EPI_RESIDUAL);
+        vb_enc_layer_qkv_dev(e, l, x, M, logical_start, kb, vb, cache_len);
+        vb_enc_layer_rest_dev(e, l, x, M, kb, vb, cache_len);
         /* new tail = last `keep` rows of this layer's K/V */
         if (!update_tail) continue;
         VB_CUDA_OK(cudaMemcpyAsync(tk, kb + (size_t)(total - keep) * VB_ENC_ATT, keep * row, cudaMemcpyDeviceToDevice, e->stream));
@@ -117,6 +134,34 @@ int vox_cuda_encoder_step(vox_ctx_t *ctx, float *d_x, int new_len) {
     if (ctx->enc_kv_cache_len > ctx->enc_kv_cache_max) ctx->enc_kv_cache_max = ctx->enc_kv_cache_len;
     return 0;
 }
+
+/* ---- building blocks for a sequence-sharded encoder run (all pointers are DEVICE pointers; see tools/sharded_encode.py) ---- */
+int vox_cuda_mel_conv_stem(vox_ctx_t *ctx, const float *d_pcm_padded_mel /* [F,128] mel frames */, int mel_frames, float *d_out) {
+    VbEngine *e = vb_engine(ctx);
+    int n = 0;
+    vb_conv_stem_full_dev(e, d_pcm_padded_mel, mel_frames, d_out, &n);
+    return n;
+}
+int vox_cuda_encoder_layer_qkv(vox_ctx_t *ctx, int layer, const float *d_x, int M, int pos0, float *d_k, float *d_v, int row_off) {
+    if (layer < 0 || layer >= VOX_ENC_LAYERS || M <= 0) return -1;
+    vb_enc_layer_qkv_dev(vb_engine(ctx), layer, d_x, M, pos0, d_k, d_v, row_off);
+    return 0;
+}
+int vox_cuda_encoder_layer_rest(vox_ctx_t *ctx, int layer, float *d_x, int M, const float *d_k, const float *d_v, int q_off) {
+    if (layer < 0 || layer >= VOX_ENC_LAYERS || M <= 0) return -1;
+    vb_enc_layer_rest_dev(vb_engine(ctx), layer, d_x, M, d_k, d_v, q_off);
+    return 0;
+}
+int vox_cuda_encoder_final_norm(vox_ctx_t *ctx, float *d_x, int M) {
+    VbEngine *e = vb_engine(ctx);
+    vb_rmsnorm_rows(e, d_x, d_x, e->d_enc_norm, nullptr, M, ENC_DIM, VOX_ENC_NORM_EPS);
+    return 0;
+}
+int vox_cuda_adapter(vox_ctx_t *ctx, const float *d_enc, int enc_len, float *d_out) {
+    vb_adapter_dev(vb_engine(ctx), d_enc, enc_len, d_out);
+    return enc_len / VOX_DOWNSAMPLE;
+}
+void vox_cuda_sync(vox_ctx_t *ctx) { VB_CUDA_OK(cudaStreamSynchronize(vb_engine(ctx)->stream)); }
 
 float *vox_encoder_forward_incremental(vox_ctx_t *ctx, const float *x_new, int new_len, int *out_len) {
     if (new_len <= 0) { *out_len = 0; return NULL; }

@@ -157,6 +157,8 @@ int  vb_decoder_persist_launch(VbEngine *e, const float *d_adapter, int adapter_
 /* vb_encoder.cu */
 void vb_encoder_layers_dev(VbEngine *e, float *d_x, int new_len, int cache_len, int logical_start, int update_tail);
 void vb_adapter_dev(VbEngine *e, const float *d_enc, int enc_len, float *d_out);
+void vb_enc_layer_qkv_dev(VbEngine *e, int l, const float *x, int M, int pos0, float *kb, float *vb, int row_off);
+void vb_enc_layer_rest_dev(VbEngine *e, int l, float *x, int M, const float *kb, const float *vb, int q_off);
 void vb_conv_view_dev(VbEngine *e, const float *in, int cin, int stride, int n_out,
                       const uint16_t *w_kc, const float *bias, float *out, int cout);
 

@@ -756,6 +756,16 @@ int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out) {
     return 0;
 }
 
+float *vox_cuda_mel_device_frames(vox_mel_ctx_t *mel, int *n_frames) {
+    int off = 0;
+    return vb_mel_dev_frames(mel, n_frames, &off);
+}
+int vox_cuda_mel_feed_zeros(vox_mel_ctx_t *mel, int n) { return vb_mel_feed_zeros(mel, n); }
+int vox_cuda_build_prompt(vox_ctx_t *ctx, float *d_out, const float *d_adapter, int n) {
+    vb_build_prompt_dev(vb_engine(ctx), d_out, d_adapter, n, TOKEN_BOS, TOKEN_STREAMING_PAD);
+    return 0;
+}
+
 void vox_cuda_set_decode_mode(vox_ctx_t *ctx, int mode) {
     if (ctx) vb_engine(ctx)->decode_mode = mode;
 }
