@@ -404,6 +404,11 @@ int   vox_cuda_memcpy_d2h(vox_ctx_t *ctx, void *h_dst, const void *d_src, size_t
 void   vox_cuda_timer_start(vox_ctx_t *ctx);
 double vox_cuda_timer_stop_ms(vox_ctx_t *ctx);
 
+/* Test hooks: copy one decoder layer's KV ring ([8192][1024] f32 each, slot = position & 8191) or the last step's logits
+ * ([131072] f32) to host memory. */
+int vox_cuda_debug_copy_kv(vox_ctx_t *ctx, int layer, float *h_k, float *h_v);
+int vox_cuda_debug_copy_logits(vox_ctx_t *ctx, float *h_logits);
+
 /* Copy the device stream state a test wants to inspect back to the host. */
 int vox_cuda_stream_token_ids(vox_stream_t *s, int *out, int max);   /* all ids generated so far */
 int vox_cuda_stream_counts(vox_stream_t *s, int *mel_frames, int *adapter_tokens,

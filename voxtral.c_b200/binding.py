@@ -97,7 +97,8 @@ def lib():
         "vox_cuda_encoder_layer_qkv": (i, [vp, i, vp, i, i, vp, vp, i]),
         "vox_cuda_encoder_layer_rest": (i, [vp, i, vp, i, vp, vp, i]),
         "vox_cuda_encoder_final_norm": (i, [vp, vp, i]), "vox_cuda_adapter": (i, [vp, vp, i, vp]),
-        "vox_cuda_sync": (None, [vp]), "vox_cuda_mel_device_frames": (vp, [vp, c_int_p]),
+        "vox_cuda_sync": (None, [vp]), "vox_cuda_debug_copy_kv": (i, [vp, i, c_float_p, c_float_p]),
+        "vox_cuda_debug_copy_logits": (i, [vp, c_float_p]), "vox_cuda_mel_device_frames": (vp, [vp, c_int_p]),
         "vox_cuda_mel_feed_zeros": (i, [vp, i]), "vox_cuda_build_prompt": (i, [vp, vp, vp, i]),
         "vox_cuda_decoder_prefill": (i, [vp, vp, i]), "vox_cuda_decoder_steps": (i, [vp, vp, i, i, i, c_int_p]),
         "vox_cuda_encoder_step": (i, [vp, vp, i]),

@@ -766,6 +766,21 @@ int vox_cuda_build_prompt(vox_ctx_t *ctx, float *d_out, const float *d_adapter, 
     return 0;
 }
 
+int vox_cuda_debug_copy_kv(vox_ctx_t *ctx, int layer, float *h_k, float *h_v) {
+    VbEngine *e = vb_engine(ctx);
+    if (!e->d_kv_k || layer < 0 || layer >= VOX_DEC_LAYERS) return -1;
+    size_t n = (size_t)VB_KV_SLOTS * VB_DEC_KV;
+    vb_d2h_sync(e, h_k, e->d_kv_k + (size_t)layer * n, n * 4);
+    vb_d2h_sync(e, h_v, e->d_kv_v + (size_t)layer * n, n * 4);
+    return 0;
+}
+int vox_cuda_debug_copy_logits(vox_ctx_t *ctx, float *h_logits) {
+    VbEngine *e = vb_engine(ctx);
+    if (!e->d_logits) return -1;
+    vb_d2h_sync(e, h_logits, e->d_logits, (size_t)VOX_VOCAB_SIZE * 4);
+    return 0;
+}
+
 void vox_cuda_set_decode_mode(vox_ctx_t *ctx, int mode) {
     if (ctx) vb_engine(ctx)->decode_mode = mode;
 }
