@@ -187,7 +187,7 @@ class Engine:
         return lib().vox_cuda_timer_stop_ms(self.ctx)
 
     def set_decode_mode(self, mode):
-        lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "mega": 2, "persist": 3}[mode])
+        lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "mega": 2, "persist": 3, "tc": 4}[mode])
 
     def reset_caches(self):
         lib().vox_cuda_reset_caches(self.ctx)

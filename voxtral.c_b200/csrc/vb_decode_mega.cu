@@ -438,6 +438,26 @@ void vb_mega_prof_report(VbEngine *e, const MegaArgs &a, const char *label) {
         for (int k = 0; k < 10; k++) { fprintf(stderr, " %s=%.0f", names[k], sum[k] / (VOX_DEC_LAYERS - 2)); tot += sum[k]; }
         fprintf(stderr, " | layer=%.0f | logits=%lld bar=%lld step=%lld\n", tot / (VOX_DEC_LAYERS - 2),
                 t[26 * 10 + 1] - t[26 * 10], t[26 * 10 + 2] - t[26 * 10 + 1], t[26 * 10 + 2] - t[0]);
+        if (!strcmp(label, "tc-ring")) {               /* producer lead (chunks) at each stamp, mean over layers */
+            fprintf(stderr, "[%s prof] cta %3d ring lead at stamp:", label, ctas[ci]);
+            for (int k = 0; k < 10; k++) {
+                double s = 0;
+                for (int l = 1; l < VOX_DEC_LAYERS - 1; l++) s += (double)t[MK_PROF_SLOTS / 2 + l * 10 + k];
+                fprintf(stderr, " %d:%.1f", k, s / (VOX_DEC_LAYERS - 2));
+            }
+            fprintf(stderr, " | producer: %lld chunks, %.0f cycles/chunk of which %.0f waiting for a free slot\n", t[MK_PROF_SLOTS - 3],
+                    (double)t[MK_PROF_SLOTS - 2] / (double)t[MK_PROF_SLOTS - 3], (double)t[MK_PROF_SLOTS - 1] / (double)t[MK_PROF_SLOTS - 3]);
+        }
+    }
+    if (!strcmp(label, "tc-ring") && getenv("VOX_CUDA_MEGA_PROF_ALL")) {
+        /* per CTA: SM id, cycles in the logits phase, summed cycles of the four GEMV phases of layers 1..24 */
+        for (int c = 0; c < e->sm_count; c++) {
+            long long *t = h + (size_t)c * MK_PROF_SLOTS;
+            double ph = 0;
+            for (int l = 1; l < VOX_DEC_LAYERS - 1; l++)
+                ph += (double)((t[l * 10 + 1] - t[l * 10]) + (t[l * 10 + 5] - t[l * 10 + 4]) + (t[l * 10 + 7] - t[l * 10 + 6]) + (t[l * 10 + 9] - t[l * 10 + 8]));
+            fprintf(stderr, "[tc-ring sm] cta %3d smid %3lld logits %lld phases/layer %.0f\n", c, t[MK_PROF_SLOTS - 4], t[26 * 10 + 1] - t[26 * 10], ph / (VOX_DEC_LAYERS - 2));
+        }
     }
     free(h);
 }

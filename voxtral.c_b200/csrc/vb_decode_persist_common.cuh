@@ -11,7 +11,7 @@
 #define MK_GROUP     16                        /* rows per reduction group */
 #define MK_SPIN_LIMIT (4000000000ll)           /* ~2 s of SM clocks: trap instead of hanging the GPU */
 #define MK_ATT_FLOATS (16 * 4 * 132)           /* intra-CTA attention merge scratch: 16 warps x 4 heads x (m,l,pad,pad,o[128]) */
-#define MK_PROF_SLOTS 512                      /* timestamps per CTA */
+#define MK_PROF_SLOTS 1024                     /* timestamps per CTA */
 
 struct MegaArgs {
     DecParams p;
@@ -21,6 +21,7 @@ struct MegaArgs {
     long long *prof;                            /* optional: per-CTA phase timestamps of step `prof_step` (else NULL) */
     int prof_step;
     int l2_ahead;                               /* bytes per CTA kept prefetched into L2 ahead of consumption */
+    const uint16_t *emb_img;                    /* tc kernel only: decode-tiled image of the tied embedding (p.tok_emb stays row-major for lookups) */
 };
 
 #define PROF(tag) do { if (a.prof && step == a.prof_step && tid == 0 && prof_n < MK_PROF_SLOTS) \

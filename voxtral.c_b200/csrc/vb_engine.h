@@ -102,8 +102,9 @@ typedef struct VbEngine {
     int *d_tokens;  int tokens_cap;
     int *h_tokens_pinned;
     float *d_embed_in;                          /* [3072] staging for the host-pointer API */
+    uint16_t *d_tc_img;                         /* decode-tiled copy of the decoder matrices for the tensor-core ring kernel (vb_decode_tc.cu) */
     unsigned int *d_mega_bar;                   /* grid-barrier counter + error word of the persistent kernel */
-    int decode_mode;                            /* 0 = auto, 1 = CUDA-graph phases, 2 = persistent kernel with TMA weight ring, 3 = persistent kernel, direct loads + L2 prefetch */
+    int decode_mode;                            /* 0 = auto, 1 = CUDA-graph phases, 2 = persistent kernel with TMA weight ring, 3 = persistent kernel, direct loads, 4 = persistent kernel, TMA ring + mma.sync consumer */
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
 
@@ -151,6 +152,8 @@ int  vb_decoder_mega_supported(VbEngine *e);
 int  vb_decoder_mega_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 
 /* vb_decode_persist.cu */
+int  vb_decoder_tc_supported(VbEngine *e);
+int  vb_decoder_tc_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 int  vb_decoder_persist_supported(VbEngine *e);
 int  vb_decoder_persist_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 
