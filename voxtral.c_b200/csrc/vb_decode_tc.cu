@@ -88,9 +88,8 @@ struct ChunkCursor {
 
 /* all 32 lanes of the producer warp run this; lane r copies row r of the chunk */
 __device__ void tc_producer(uint8_t *slots, TcSmem *sm, const DecParams &p, const uint16_t *emb_img, int n_steps, int *err,
-                            uint32_t &it_out, long long *prof, int pace) {
+                            uint32_t &it_out, long long *prof) {
     const int lane = threadIdx.x & 31;
-    long long next_t = 0;                       /* pacing: earliest clock at which the next chunk may be issued */
     ChunkCursor cur;
     cur.start(p, emb_img);
     uint32_t it = 0;
@@ -109,15 +108,6 @@ __device__ void tc_producer(uint8_t *slots, TcSmem *sm, const DecParams &p, cons
         t_wait += clock64() - tw0;
         if (aborted) break;
         const int gr = min(MK_GROUP, cur.f.nrows - cur.g0);
-        if (pace) {
-            /* Rate limit: no SM may draw more than its fair share of HBM (pace = clocks per 32 KB), with a credit of two
-             * chunks.  Unpaced, SMs close to the memory partitions stream 10-15% faster than the others, every phase ends
-             * at the pace of the slowest SM and the fast ones idle in the grid barrier (profiles/r01_decode.md). */
-            long long now = clock64();
-            while (now < next_t) now = clock64();
-            if (next_t < now - 2ll * pace) next_t = now - 2ll * pace;
-            next_t += (long long)pace * gr / MK_GROUP;
-        }
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)gr * TK_ROW_BYTES;
             mbar_expect_tx(&sm->full[s], bytes);
@@ -251,7 +241,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_dec_tc(MegaArgs a) {
     if (tid >= MK_CONS) {
         /* ===================== producer warp ===================== */
         uint32_t it = 0;
-        tc_producer(slots, sm, p, a.emb_img, a.n_steps, a.err, it, a.prof, a.l2_ahead);
+        tc_producer(slots, sm, p, a.emb_img, a.n_steps, a.err, it, a.prof);
         /* every bulk copy that was issued must land before the CTA may exit (smem is its target) */
         for (int back = 1; back <= TK_SLOTS; back++) {
             if (it < (uint32_t)back) break;
@@ -519,8 +509,7 @@ extern "C" int vb_decoder_tc_launch(VbEngine *e, const float *d_adapter, int ada
     a.emb_img = g_tc_tab.emb;
     a.n_steps = n_steps; a.pos0 = pos; a.token0 = prev_token; a.adapter_row0 = adapter_row;
     a.bar = e->d_mega_bar; a.err = (int *)(e->d_mega_bar + 32);
-    const char *pace = getenv("VOX_CUDA_TC_PACE");
-    a.l2_ahead = pace ? atoi(pace) : 0;                      /* this kernel reuses the field: producer pacing, clocks per 32 KB chunk */
+    a.l2_ahead = 0;
     vb_mega_prof_begin(e, a, n_steps);
     void *args[] = { &a };
     VB_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_dec_tc, dim3(e->sm_count), dim3(TK_THREADS), args, tc_smem_bytes(), e->stream));
