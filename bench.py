@@ -145,6 +145,12 @@ def reference_sample(model_dir, seconds, enc_positions=64, dec_steps=6):
                        f"extrapolated to the {seconds:g} s recording ({steps} steps, {pos} positions)")}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of k_dec_persist from one `ncu --set full` capture, divided by the 385 steps of
+# that launch (KV positions 38..423, so almost no KV traffic).  Not measured by this script: ncu cannot run inside a timed bench.
+NCU_DRAM_BYTES_PER_STEP = 6.56e9 + 0.95e6
+NCU_TRAFFIC_SOURCE = "profiles/r01_decode.md (ncu --set full, 30 s clip, per step)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -276,7 +282,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "x real-time", "h2d_bytes_per_step": int(pcm.nbytes),
                     "d2h_bytes_per_step": int(4 * n_dec)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "decoder step (26 layers of GEMV + attention + logits GEMV)",
+                         "traffic": NCU_DRAM_BYTES_PER_STEP, "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "kernel": "decoder step (26 layers of GEMV + attention + logits GEMV)",
                          "bytes_per_step": bytes_per_step, "peak_source": peak_src},
             "cpu_baseline": ({"value": cpu["rtf"], "unit": "x real-time", "cores": cpu["cores"], "kind": "reference",
                               "sample": cpu["sample"], "decoder_tok_s": cpu["tok_s"]} if cpu else None),
