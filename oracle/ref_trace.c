@@ -117,9 +117,17 @@ int vox_decoder_forward(vox_ctx_t *ctx, const float *input_embeds, float *logits
 }
 
 int main(int argc, char **argv) {
-    if (argc < 4) { fprintf(stderr, "usage: %s <model_dir> <wav> <out_dir> [feed_chunk_samples]\n", argv[0]); return 2; }
+    if (argc < 4) {
+        fprintf(stderr, "usage: %s <model_dir> <wav> <out_dir> [feed_chunk_samples]\n"
+                        "  scenario knobs (environment): TRACE_DELAY_MS, TRACE_FLUSH_AFTER_CHUNK, TRACE_ALT_N + TRACE_ALT_CUTOFF,\n"
+                        "  TRACE_CONTINUOUS, TRACE_INTERVAL\n", argv[0]);
+        return 2;
+    }
     g_dir = argv[3];
     int chunk = argc > 4 ? atoi(argv[4]) : 0;
+    const char *e_delay = getenv("TRACE_DELAY_MS"), *e_flush = getenv("TRACE_FLUSH_AFTER_CHUNK"), *e_alt = getenv("TRACE_ALT_N");
+    const char *e_cut = getenv("TRACE_ALT_CUTOFF"), *e_cont = getenv("TRACE_CONTINUOUS"), *e_int = getenv("TRACE_INTERVAL");
+    const int n_alt = e_alt ? atoi(e_alt) : 1;
     uint32_t r = 0xC0FFEEu;
     for (int k = 0; k < N_PROBE; k++) { r = r * 1664525u + 1013904223u; probe_ids[k] = (int)((r >> 8) % VOX_VOCAB_SIZE); }
     f_tokens = open_out("tokens.i32"); f_topv = open_out("logits_top.f32"); f_topi = open_out("logits_top.i32");
@@ -131,20 +139,41 @@ int main(int argc, char **argv) {
     int n = 0;
     float *pcm = vox_load_wav(argv[2], &n);
     if (!pcm) return 1;
+    if (e_delay) vox_set_delay(ctx, atoi(e_delay));
     vox_stream_t *s = vox_stream_init(ctx);
     if (!s) return 1;
-    /* text pieces, in order, for the text-level golden */
+    if (e_int) vox_set_processing_interval(s, (float)atof(e_int));
+    if (e_cont) vox_stream_set_continuous(s, atoi(e_cont));
+    if (n_alt > 1) vox_stream_set_alt(s, n_alt, e_cut ? (float)atof(e_cut) : 0.5f);
+    /* text pieces, in order, for the text-level golden; with alternatives: one line per position, fields separated by TAB,
+     * and text.txt keeps the best piece only.  drain.txt records how many positions each drain returned. */
     FILE *ftext = open_out("text.txt");
-    const char *toks[64];
+    FILE *falt = open_out("alt.txt");
+    FILE *fdrain = open_out("drain.txt");
+    const char *toks[64 * 8];
     int got;
+#define DRAIN(tag) do { \
+        int total = 0; \
+        if (n_alt > 1) { \
+            while ((got = vox_stream_get_alt(s, toks, 64, n_alt)) > 0) { total += got; \
+                for (int i = 0; i < got; i++) { \
+                    fputs(toks[i * n_alt], ftext); \
+                    for (int k = 0; k < n_alt; k++) { if (k) fputc('\t', falt); fputs(toks[i * n_alt + k] ? toks[i * n_alt + k] : "<null>", falt); } \
+                    fputc('\n', falt); } } \
+        } else while ((got = vox_stream_get(s, toks, 64)) > 0) { total += got; for (int i = 0; i < got; i++) fputs(toks[i], ftext); } \
+        fprintf(fdrain, "%s %d\n", tag, total); } while (0)
     if (chunk <= 0) vox_stream_feed(s, pcm, n);
-    else for (int off = 0; off < n; off += chunk) {
-        vox_stream_feed(s, pcm + off, n - off < chunk ? n - off : chunk);
-        while ((got = vox_stream_get(s, toks, 64)) > 0) for (int i = 0; i < got; i++) fputs(toks[i], ftext);
+    else {
+        int ci = 0;
+        for (int off = 0; off < n; off += chunk, ci++) {
+            vox_stream_feed(s, pcm + off, n - off < chunk ? n - off : chunk);
+            DRAIN("feed");
+            if (e_flush && ci == atoi(e_flush)) { vox_stream_flush(s); DRAIN("flush"); }
+        }
     }
     vox_stream_finish(s);
-    while ((got = vox_stream_get(s, toks, 64)) > 0) for (int i = 0; i < got; i++) fputs(toks[i], ftext);
-    fclose(ftext);
+    DRAIN("finish");
+    fclose(ftext); fclose(falt); fclose(fdrain);
     vox_stream_free(s);
 
     FILE *fj = open_out("trace.json");

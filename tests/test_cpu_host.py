@@ -188,3 +188,83 @@ def test_goldens_are_consistent():
         n_adapter = sum(int(g[f"adapter_{k}_shape"][0]) for k in range(int(g["n_adapter_calls"])))
         assert n_adapter == 74 and n_adapter - 38 == 36
     assert np.array_equal(golden("synth_s2_oneshot")["tokens"], golden("synth_s2_chunk1s")["tokens"])
+
+
+def _both(vb, ref):
+    return (("engine", vb.lib()), ("reference", ref.L))
+
+
+def test_tokenizer_sequence_and_specials_match_reference(vb, ref, tmp_path):
+    """vox_tokenizer_decode_seq / _bos / _eos / _vocab_size (voxtral_tokenizer.c) against the compiled reference."""
+    subprocess.check_call([os.sys.executable, os.path.join(ROOT, "tools", "make_synth_tekken.py"), str(tmp_path)])
+    path = str(tmp_path / "tekken.json").encode()
+    seq = np.array([1, 32, 1064, 1100, 1255, 33, 5000, 1000, 1256, 77777, 2, 1300], np.int32)
+    got = {}
+    for name, L in _both(vb, ref):
+        L.vox_tokenizer_load.restype = C.c_void_p; L.vox_tokenizer_load.argtypes = [C.c_char_p]
+        L.vox_tokenizer_decode_seq.restype = C.c_void_p; L.vox_tokenizer_decode_seq.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+        for fn in ("vox_tokenizer_bos", "vox_tokenizer_eos", "vox_tokenizer_vocab_size"):
+            getattr(L, fn).restype = C.c_int; getattr(L, fn).argtypes = [C.c_void_p]
+        t = L.vox_tokenizer_load(path)
+        assert t
+        p = L.vox_tokenizer_decode_seq(t, seq.ctypes.data_as(C.POINTER(C.c_int)), seq.size)
+        got[name] = (C.string_at(p), L.vox_tokenizer_bos(t), L.vox_tokenizer_eos(t), L.vox_tokenizer_vocab_size(t),
+                     C.string_at(L.vox_tokenizer_decode_seq(t, seq.ctypes.data_as(C.POINTER(C.c_int)), 0)))
+    assert got["engine"] == got["reference"]
+    assert got["engine"][1:3] == (1, 2)
+
+
+def test_wav_buffer_parser_matches_reference(vb, ref, tmp_path):
+    """vox_parse_wav_buffer (voxtral_audio.c): a good stereo 22.05 kHz file, a truncated one, and garbage."""
+    rng = np.random.default_rng(5)
+    p = tmp_path / "b.wav"
+    _write_wav(p, 22050, 2, rng.integers(-15000, 15000, size=(2500, 2)))
+    blob = p.read_bytes()
+    u8p = C.POINTER(C.c_uint8)
+    for data in (blob, blob[:len(blob) // 2], blob[:30], b"RIFFxxxxWAVEjunk" + bytes(64), bytes(100)):
+        res = {}
+        for name, L in _both(vb, ref):
+            L.vox_parse_wav_buffer.restype = fp; L.vox_parse_wav_buffer.argtypes = [u8p, C.c_size_t, C.POINTER(C.c_int)]
+            n = C.c_int(-7)
+            buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+            out = L.vox_parse_wav_buffer(buf, len(data), C.byref(n))
+            res[name] = None if not out else np.ctypeslib.as_array(out, shape=(n.value,)).copy()
+        assert (res["engine"] is None) == (res["reference"] is None), len(data)
+        if res["engine"] is not None:
+            assert res["engine"].shape == res["reference"].shape
+            assert np.abs(res["engine"] - res["reference"]).max() < 2e-3     # 22.05 kHz taps, see test_wav_loader_matches_reference
+
+
+@pytest.mark.parametrize("kind", ["raw", "wav"])
+def test_read_pcm_stdin_matches_reference(vb, ref, tmp_path, kind):
+    """vox_read_pcm_stdin (voxtral_audio.c): raw s16le 16 kHz mono, or a WAV container, detected from the first bytes."""
+    rng = np.random.default_rng(9)
+    pcm = rng.integers(-12000, 12000, size=4097).astype("<i2")
+    src = tmp_path / "in.bin"
+    if kind == "raw":
+        src.write_bytes(pcm.tobytes())
+    else:
+        _write_wav(src, 16000, 1, pcm)
+    outs = {}
+    for name, lib in (("engine", os.path.join(ROOT, "voxtral.c_b200", "libvoxtral_b200.so")), ("reference", ref.L._name)):
+        code = ("import ctypes as C, numpy as np, sys; L = C.CDLL(%r); L.vox_read_pcm_stdin.restype = C.POINTER(C.c_float); "
+                "n = C.c_int(); p = L.vox_read_pcm_stdin(C.byref(n)); "
+                "sys.stdout.buffer.write(np.ctypeslib.as_array(p, shape=(n.value,)).tobytes() if p else b'')") % lib
+        with open(src, "rb") as f:
+            r = subprocess.run([os.sys.executable, "-c", code], stdin=f, capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()[-500:]
+        outs[name] = np.frombuffer(r.stdout, np.float32)
+    assert outs["engine"].size == outs["reference"].size == 4097
+    assert np.abs(outs["engine"] - outs["reference"]).max() < 2e-6
+
+
+def test_mic_stubs_behave_like_the_reference_off_macos(vb, ref):
+    """voxtral_mic_macos.c:124-142: on anything but macOS start fails with -1, reads return 0 samples."""
+    for name, L in _both(vb, ref):
+        if not hasattr(L, "vox_mic_start"):
+            assert name == "reference"          # the reference library is built from the model sources only
+            continue
+        buf = (C.c_float * 16)()
+        assert L.vox_mic_start() == -1
+        assert L.vox_mic_read(buf, 16) == 0 and L.vox_mic_read_available() == 0
+        L.vox_mic_stop()

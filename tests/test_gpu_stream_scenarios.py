@@ -1,0 +1,93 @@
+"""Stream-API scenarios beyond plain feeding, each against a trace of the UNMODIFIED reference on the same seeded checkpoint and
+PCM (oracle/ref_trace.c with its TRACE_* knobs; fixtures under tests/golden/, made by tools/make_goldens.py):
+  delay240 : vox_set_delay(240 ms) -> 3 delay tokens, a 36-row prompt, a different time conditioning (voxtral.c:1538-1560)
+  flush    : 0.5 s feeds, vox_stream_flush() after the second -> the decoder runs ahead over padding (voxtral.c:1280-1316);
+             the number of positions every drain returns must match, not only the final ids
+  alt3     : vox_stream_set_alt(3, 0.9) + vox_stream_get_alt (voxtral.c:1009-1046)
+plus the convenience entry points (vox_transcribe*, cache preallocation)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, read_wav_f32, synth_wav
+from test_gpu_stream_parity import check_against
+
+pytestmark = pytest.mark.gpu
+
+
+def test_delay_240ms_matches_reference(engine):
+    g = golden("synth_s2_delay240")
+    pcm = read_wav_f32(synth_wav(2))
+    engine.set_delay(240)
+    try:
+        s = engine.stream(); s.feed(pcm); s.finish()
+        text = b"".join(s.get()); ids = s.token_ids().copy(); counts = s.counts(); s.close()
+    finally:
+        engine.set_delay(480)
+    assert counts["adapter_tokens"] == 71
+    check_against(g, ids, text)
+
+
+def test_flush_midstream_matches_reference(engine):
+    g = golden("synth_s2_flush")
+    pcm = read_wav_f32(synth_wav(2))
+    chunk = int(g["feed_chunk"])
+    assert chunk == 8000
+    s = engine.stream()
+    drains, pieces = [], []
+    for ci, off in enumerate(range(0, pcm.size, chunk)):
+        s.feed(pcm[off:off + chunk])
+        got = s.get(); drains.append(("feed", len(got))); pieces += got
+        if ci == 1:
+            assert s.flush() == 0
+            got = s.get(); drains.append(("flush", len(got))); pieces += got
+    s.finish()
+    got = s.get(); drains.append(("finish", len(got))); pieces += got
+    ids = s.token_ids().copy(); s.close()
+    want = list(zip([str(t) for t in g["drain_tag"]], [int(n) for n in g["drain_n"]]))
+    print("drains", drains)
+    assert drains == want
+    check_against(g, ids, b"".join(pieces))
+
+
+def test_alternatives_match_reference(engine):
+    g = golden("synth_s2_alt3")
+    pcm = read_wav_f32(synth_wav(2))
+    s = engine.stream()
+    s.set_alt(3, 0.9)
+    s.feed(pcm); s.finish()
+    rows = s.get_alt(3)
+    ids = s.token_ids().copy(); s.close()
+    check_against(g, ids, b"".join(r[0] for r in rows))
+    want = [l.split(b"\t") for l in g["alt"].tobytes().split(b"\n") if l]
+    assert len(rows) == len(want) == 36
+    # an alternative qualifies if 1 - p_i/p_0 <= cutoff; p ratios come from logits that agree to ~2e-6, so only a candidate
+    # sitting exactly on the cutoff could differ -- none does on this clip
+    for i, (r, w) in enumerate(zip(rows, want)):
+        assert [x if x is not None else b"<null>" for x in r] == w, i
+
+
+def test_transcribe_entry_points_agree_with_the_stream_api(engine, vb, model_dir):
+    wav = synth_wav(2)
+    pcm = read_wav_f32(wav)
+    s = engine.stream(); s.feed(pcm); s.finish(); want = b"".join(s.get()); s.close()
+    L = vb.lib()
+    p = L.vox_transcribe(engine.ctx, wav.encode())
+    assert p and C.string_at(p) == want
+    p2 = L.vox_transcribe_audio(engine.ctx, pcm.ctypes.data_as(C.POINTER(C.c_float)), pcm.size)
+    assert p2 and C.string_at(p2) == want
+    assert not L.vox_transcribe(engine.ctx, b"/nonexistent.wav")
+    assert L.vox_decoder_kv_cache_preallocate(engine.ctx, 4096) == 0 and L.vox_encoder_kv_cache_preallocate(engine.ctx, 4096) == 0
+    s = engine.stream(); s.feed(pcm); s.finish(); again = b"".join(s.get()); s.close()
+    assert again == want
+    # vox_transcribe_stdin reads fd 0 of its own process
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); import vbload; vb = vbload.load(); e = vb.Engine(%r); "
+            "p = vb.lib().vox_transcribe_stdin(e.ctx); sys.stdout.buffer.write(b'TEXT:' + (C.string_at(p) if p else b'<null>')); e.close()") % (ROOT, model_dir)
+    with open(wav, "rb") as f:
+        r = subprocess.run([sys.executable, "-c", code], stdin=f, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-1500:]
+    assert r.stdout.split(b"TEXT:")[-1] == want

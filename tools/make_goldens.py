@@ -47,6 +47,14 @@ def main(trace, name):
     se = f32("step_embed.f32", 3072)
     for kk, v in rows_digest(se, keep=(0, 1, 2, -1)).items():
         out[f"step_embed_{kk}"] = v
+    # scenario traces (TRACE_* knobs of ref_trace): how many positions each drain returned, and the alternatives table
+    dp = os.path.join(trace, "drain.txt")
+    if os.path.exists(dp):
+        rows = [l.split() for l in open(dp).read().splitlines() if l.strip()]
+        out["drain_tag"] = np.array([r[0] for r in rows]); out["drain_n"] = np.array([int(r[1]) for r in rows], dtype=np.int32)
+    ap = os.path.join(trace, "alt.txt")
+    if os.path.exists(ap) and os.path.getsize(ap):
+        out["alt"] = np.frombuffer(open(ap, "rb").read(), dtype=np.uint8)
     out["n_encoder_calls"] = np.array(man["encoder_calls"])
     out["n_adapter_calls"] = np.array(man["adapter_calls"])
     dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", name + ".npz")

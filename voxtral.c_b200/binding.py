@@ -58,6 +58,8 @@ def lib():
         "vox_stream_finish": (i, [vp]), "vox_stream_flush": (i, [vp]),
         "vox_stream_get": (i, [vp, C.POINTER(C.c_char_p), i]),
         "vox_stream_get_alt": (i, [vp, C.POINTER(C.c_char_p), i, i]),
+        "vox_transcribe": (vp, [vp, C.c_char_p]), "vox_transcribe_stdin": (vp, [vp]),
+        "vox_decoder_kv_cache_preallocate": (i, [vp, i]), "vox_encoder_kv_cache_preallocate": (i, [vp, i]),
         "vox_stream_set_alt": (None, [vp, i, f]), "vox_set_processing_interval": (None, [vp, f]),
         "vox_stream_set_continuous": (None, [vp, i]), "vox_stream_free": (None, [vp]),
         "vox_transcribe_audio": (vp, [vp, c_float_p, i]),
@@ -186,6 +188,9 @@ class Engine:
     def timer_stop_ms(self):
         return lib().vox_cuda_timer_stop_ms(self.ctx)
 
+    def set_delay(self, delay_ms):
+        lib().vox_set_delay(self.ctx, int(delay_ms))
+
     def set_decode_mode(self, mode):
         lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "mega": 2, "persist": 3, "tc": 4}[mode])
 
@@ -245,6 +250,17 @@ class Stream:
 
     def set_alt(self, n_alt, cutoff):
         lib().vox_stream_set_alt(self.s, n_alt, cutoff)
+
+    def get_alt(self, n_alt):
+        """[[best, alt1, ...], ...] per token position; missing alternatives are None (voxtral.h:264-269)."""
+        out = []
+        buf = (C.c_char_p * (64 * n_alt))()
+        while True:
+            n = lib().vox_stream_get_alt(self.s, buf, 64, n_alt)
+            if n <= 0:
+                break
+            out.extend([buf[i * n_alt + k] for k in range(n_alt)] for i in range(n))
+        return out
 
     def get(self):
         out = []
