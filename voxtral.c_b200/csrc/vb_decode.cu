@@ -488,3 +488,58 @@ extern "C" void vb_decoder_prefill_dev(VbEngine *e, const float *d_embeds, int n
         vb_gemm_bf16w(e, g, DEC_HID, e->dec[l].w2, nullptr, x, DEC_DIM, n, DEC_DIM, DEC_HID, VB_EPI_RESIDUAL);
     }
 }
+
+
+/* ---------------------------------------------------------------- alternatives (vox_stream_set_alt) on the device */
+/* What stream_fill_alts() needs from a step's 131072 logits (voxtral.c:911-966): Z = sum_i exp(l_i - l_best) and the
+ * (up to) three largest text-range logits other than the best token, first index winning ties.  One CTA re-reads the
+ * logits from L2 (512 KB) instead of shipping them to the host for a 131072-wide expf loop. */
+#define ALT_THREADS 1024
+__global__ void __launch_bounds__(ALT_THREADS) k_alt_candidates(const float *__restrict__ logits, int best, int text_min,
+                                                                float *__restrict__ out /* [0]=Z, [1..3]=exp(l-l_best), [4..6]=index as float bits */) {
+    __shared__ float s_sum[ALT_THREADS / 32];
+    __shared__ unsigned long long s_best[ALT_THREADS / 32];
+    __shared__ int s_used[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float lbest = logits[best];
+    float z = 0.f;
+    for (int i = tid; i < VOX_VOCAB_SIZE; i += ALT_THREADS) z += expf(logits[i] - lbest);
+    z = vb_warp_sum(z);
+    if (lane == 0) s_sum[warp] = z;
+    if (tid < 3) s_used[tid] = -1;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < ALT_THREADS / 32; w++) t += s_sum[w]; out[0] = t; }
+    for (int r = 0; r < 3; r++) {
+        unsigned long long c = 0ull;
+        const int u0 = s_used[0], u1 = s_used[1];
+        for (int i = text_min + tid; i < VOX_VOCAB_SIZE; i += ALT_THREADS) {
+            if (i == best || i == u0 || i == u1) continue;
+            unsigned long long k = pack_cand(logits[i], i);
+            if (k > c) c = k;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { unsigned long long other = __shfl_xor_sync(0xffffffffu, c, o); if (other > c) c = other; }
+        if (lane == 0) s_best[warp] = c;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long m = 0ull;
+            for (int w = 0; w < ALT_THREADS / 32; w++) if (s_best[w] > m) m = s_best[w];
+            const int idx = m ? cand_index(m) : -1;
+            s_used[r] = idx;
+            out[1 + r] = idx >= 0 ? expf(logits[idx] - lbest) : 0.f;
+            out[4 + r] = __int_as_float(idx);
+        }
+        __syncthreads();
+    }
+}
+
+/* host view: z, e[3] (exp(l_i - l_best), descending), idx[3] (-1 = none) for the logits of the last decode step */
+extern "C" void vb_alt_candidates(VbEngine *e, int best, int text_min, float *z, float ev[3], int idx[3]) {
+    float *d_out = vb_ws(e, VB_WS_ALT, 8 * sizeof(float));
+    k_alt_candidates<<<1, ALT_THREADS, 0, e->stream>>>(e->d_logits, best, text_min, d_out);
+    e->launches += 1;
+    float h[8];
+    vb_d2h_sync(e, h, d_out, sizeof h);
+    *z = h[0];
+    for (int r = 0; r < 3; r++) { ev[r] = h[1 + r]; memcpy(&idx[r], &h[4 + r], 4); }
+}

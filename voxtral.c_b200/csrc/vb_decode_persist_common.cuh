@@ -1,7 +1,8 @@
 /*
- * vb_decode_persist_common.cuh -- building blocks shared by the two persistent decode kernels
- * (vb_decode_mega.cu: TMA weight ring; vb_decode_persist.cu: direct streaming loads + L2 prefetch).
- * Both run 512 compute threads per CTA that synchronise on named barrier 1.
+ * vb_decode_persist_common.cuh -- building blocks shared by the persistent decode kernels
+ * (vb_decode_persist.cu: direct streaming loads, the default; vb_decode_mega.cu: TMA weight ring + CUDA-core consumer;
+ * vb_decode_tc.cu: TMA ring over a decode-tiled weight image + mma.sync consumer).
+ * All run 512 compute threads per CTA that synchronise on named barrier 1.
  */
 #ifndef VB_DECODE_PERSIST_COMMON_CUH
 #define VB_DECODE_PERSIST_COMMON_CUH

@@ -34,6 +34,7 @@
 #define VB_KV_SLOTS  VOX_DEC_WINDOW                                    /* 8192 */
 #define VB_TOKEN_EOS 2
 #define VB_WS_SLOTS  24   /* 0-11: model blocks (see vb_encoder.cu), 12-23: stream pipeline */
+#define VB_WS_ALT    20   /* 8 floats: result of the alternatives kernel (vb_decode.cu) */
 
 #define VB_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) {                 \
     fprintf(stderr, "voxtral_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__),        \
@@ -152,6 +153,7 @@ int  vb_decoder_mega_supported(VbEngine *e);
 int  vb_decoder_mega_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 
 /* vb_decode_persist.cu */
+void vb_alt_candidates(VbEngine *e, int best, int text_min, float *z, float ev[3], int idx[3]);
 int  vb_decoder_tc_supported(VbEngine *e);
 int  vb_decoder_tc_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 int  vb_decoder_persist_supported(VbEngine *e);

@@ -70,7 +70,6 @@ struct vox_stream {
     const char **token_queue;
     int queue_head, queue_tail, queue_cap;
     int n_alt; float alt_cutoff;
-    float *logits;            /* host [131072], only touched when n_alt > 1 */
 
     int min_new_mel;
     double encoder_ms, decoder_ms, prefill_ms;
@@ -111,32 +110,22 @@ static void enqueue(vox_stream_t *s, const char *alts[VOX_MAX_ALT]) {
     s->queue_tail = next;
 }
 
-/* alternatives: softmax over the step's logits, candidates restricted to text ids, accepted
- * while 1 - p/p_best <= cutoff (voxtral.c:911-966) */
+/* Alternatives for a text position (voxtral.c:911-966): p_i = exp(l_i - l_max) / Z; the runner-up text tokens, best first,
+ * are kept while 1 - p_i / p_best <= cutoff.  Z and the three candidates come from a device kernel over the step's logits
+ * (vb_alt_candidates); l_max is the greedy token's logit, so its own exp() is exactly 1. */
 static void fill_alts(vox_stream_t *s, int best, const char *alts[VOX_MAX_ALT]) {
     memset(alts, 0, VOX_MAX_ALT * sizeof *alts);
     alts[0] = vox_tokenizer_decode(s->tokenizer, best);
     if (s->n_alt <= 1) return;
-    float *lg = s->logits, mx = lg[0], sum = 0;
-    for (int i = 1; i < VOX_VOCAB_SIZE; i++) if (lg[i] > mx) mx = lg[i];
-    for (int i = 0; i < VOX_VOCAB_SIZE; i++) { lg[i] = expf(lg[i] - mx); sum += lg[i]; }
-    float inv = 1.0f / sum;
-    for (int i = 0; i < VOX_VOCAB_SIZE; i++) lg[i] *= inv;
-    float pbest = lg[best];
-    if (pbest <= 0) return;
-    int used[VOX_MAX_ALT], found = 1;
-    used[0] = best;
-    while (found < s->n_alt) {
-        int bi = -1; float bp = -1;
-        for (int i = TOKEN_TEXT_MIN; i < VOX_VOCAB_SIZE; i++) {
-            if (i == best) continue;
-            int skip = 0;
-            for (int j = 1; j < found; j++) if (used[j] == i) { skip = 1; break; }
-            if (!skip && lg[i] > bp) { bp = lg[i]; bi = i; }
-        }
-        if (bi < 0 || 1.0f - bp / pbest > s->alt_cutoff) break;
-        used[found] = bi;
-        alts[found++] = vox_tokenizer_decode(s->tokenizer, bi);
+    float z, ev[3]; int idx[3];
+    vb_alt_candidates(s->e, best, TOKEN_TEXT_MIN, &z, ev, idx);
+    const float inv = 1.0f / z, p_best = 1.0f * inv;
+    if (!(p_best > 0)) return;
+    for (int k = 0; k + 1 < s->n_alt && k < 3; k++) {
+        if (idx[k] < 0) break;
+        const float p = ev[k] * inv;
+        if (1.0f - p / p_best > s->alt_cutoff) break;
+        alts[k + 1] = vox_tokenizer_decode(s->tokenizer, idx[k]);
     }
 }
 
@@ -356,12 +345,11 @@ static int generate(vox_stream_t *s, int n, step_stats *st) {
     if (n > s->tok_buf_cap) { s->tok_buf_cap = n + 256; s->tok_buf = realloc(s->tok_buf, sizeof(int) * (size_t)s->tok_buf_cap); }
     int produced = 0;
     while (produced < n && !s->eos_seen) {
-        int want = s->n_alt > 1 ? 1 : n - produced;      /* alternatives need each step's logits on the host */
+        int want = s->n_alt > 1 ? 1 : n - produced;      /* alternatives are taken from each step's logits (still in HBM) */
         int row = s->gen_pos - s->adapter_pos_offset;
         int pos = c->kv_pos_offset + c->kv_cache_len;
         int got = vb_decoder_run_steps(e, s->d_adapter, row, want, s->prev_token, pos, s->tok_buf);
         if (got <= 0) break;
-        if (s->n_alt > 1) vb_d2h_sync(e, s->logits, e->d_logits, (size_t)VOX_VOCAB_SIZE * 4);
         for (int i = 0; i < got; i++) {
             kv_counters_step(c);
             on_token(s, s->tok_buf[i], st);
@@ -467,7 +455,6 @@ vox_stream_t *vox_stream_init(vox_ctx_t *ctx) {
     s->queue_cap = 256;
     s->token_queue = calloc((size_t)s->queue_cap * VOX_MAX_ALT, sizeof *s->token_queue);
     s->n_alt = 1;
-    s->logits = malloc((size_t)VOX_VOCAB_SIZE * sizeof(float));
     s->d_mel_tail = vb_dev_alloc((size_t)2 * VOX_MEL_BINS * 4);
     s->d_conv0_tail = vb_dev_alloc((size_t)VOX_ENC_DIM * 4);
     s->d_conv0_resid = vb_dev_alloc((size_t)VOX_ENC_DIM * 4);
@@ -578,7 +565,7 @@ void vox_stream_free(vox_stream_t *s) {
     if (s->tokenizer) vox_tokenizer_free(s->tokenizer);
     cudaFree(s->d_adapter); cudaFree(s->d_mel_tail); cudaFree(s->d_conv0_tail);
     cudaFree(s->d_conv0_resid); cudaFree(s->d_enc_resid);
-    free(s->token_queue); free(s->logits); free(s->ids); free(s->tok_buf);
+    free(s->token_queue); free(s->ids); free(s->tok_buf);
     free(s);
 }
 
