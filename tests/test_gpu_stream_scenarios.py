@@ -91,3 +91,26 @@ def test_transcribe_entry_points_agree_with_the_stream_api(engine, vb, model_dir
         r = subprocess.run([sys.executable, "-c", code], stdin=f, capture_output=True, timeout=600)
     assert r.returncode == 0, r.stderr.decode()[-1500:]
     assert r.stdout.split(b"TEXT:")[-1] == want
+
+
+def test_continuous_mode_kv_restart_matches_reference(engine):
+    """172 s fed in 1-s pieces with vox_stream_set_continuous(1): once the decoder holds more than 2000 positions the
+    reference hard-resets the whole stream (mel, conv tails, encoder cache, adapter buffer, decoder; voxtral.c:1137-1187) and
+    starts a new prompt on the audio that follows.  Same ids, same text, same number of positions returned after every feed."""
+    g = golden("synth_s172_continuous")
+    assert int(g["n_prefills"]) >= 2, "the trace must contain at least one restart"
+    pcm = read_wav_f32(synth_wav(172))
+    chunk = int(g["feed_chunk"])
+    s = engine.stream()
+    s.set_continuous(True)
+    drains, pieces = [], []
+    for off in range(0, pcm.size, chunk):
+        s.feed(pcm[off:off + chunk])
+        got = s.get(); drains.append(len(got)); pieces += got
+    s.finish()
+    got = s.get(); drains.append(len(got)); pieces += got
+    ids = s.token_ids().copy(); s.close()
+    want = [int(n) for n in g["drain_n"]]
+    first_bad = next((i for i, (a, b) in enumerate(zip(drains, want)) if a != b), None)
+    assert drains == want, f"first differing drain: #{first_bad}: {drains[first_bad]} vs {want[first_bad]}"
+    check_against(g, ids, b"".join(pieces))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turn a oracle/_ref/ref_trace output directory into a compact fixture under tests/golden/.
 
-  python tools/make_goldens.py <trace_dir> <name>      ->  tests/golden/<name>.npz
+  python tools/make_goldens.py <trace_dir> <name> [slim]     ->  tests/golden/<name>.npz
 
 The trace comes from the UNMODIFIED reference (oracle/ref_trace.c interposes its model-block entry
 points), run in the build container on the seeded synthetic checkpoint + PCM:
@@ -25,7 +25,8 @@ def rows_digest(a, keep=(0, 1, -2, -1)):
             "rows_idx": np.array(idx), "rows": a[idx]}
 
 
-def main(trace, name):
+def main(trace, name, slim=False):
+    """slim: long traces keep ids, top-8 logits, text and drain counts only (no block digests, no probe logits)."""
     man = json.load(open(os.path.join(trace, "trace.json")))
     out = {"samples": np.array(man["samples"]), "feed_chunk": np.array(man["feed_chunk"]),
            "probe_ids": np.array(man["probe_ids"], dtype=np.int32)}
@@ -33,20 +34,23 @@ def main(trace, name):
     out["tokens"] = np.fromfile(os.path.join(trace, "tokens.i32"), dtype=np.int32)
     out["top_val"] = f32("logits_top.f32", 8)
     out["top_idx"] = np.fromfile(os.path.join(trace, "logits_top.i32"), dtype=np.int32).reshape(-1, 8)
-    out["probe_val"] = f32("logits_probe.f32", 64)
+    if not slim:
+        out["probe_val"] = f32("logits_probe.f32", 64)
     out["text"] = np.frombuffer(open(os.path.join(trace, "text.txt"), "rb").read(), dtype=np.uint8)
-    for k in range(man["encoder_calls"]):
+    for k in range(0 if slim else man["encoder_calls"]):
         for kind, w in (("enc_in", 1280), ("enc_out", 1280)):
             for kk, v in rows_digest(f32(f"{kind}_{k}.f32", w)).items():
                 out[f"{kind}_{k}_{kk}"] = v
-    for k in range(man["adapter_calls"]):
-        for kk, v in rows_digest(f32(f"adapter_{k}.f32", 3072)).items():
-            out[f"adapter_{k}_{kk}"] = v
-    for kk, v in rows_digest(f32("prefill_embed.f32", 3072)).items():
-        out[f"prefill_embed_{kk}"] = v
-    se = f32("step_embed.f32", 3072)
-    for kk, v in rows_digest(se, keep=(0, 1, 2, -1)).items():
-        out[f"step_embed_{kk}"] = v
+    if not slim:
+        for k in range(man["adapter_calls"]):
+            for kk, v in rows_digest(f32(f"adapter_{k}.f32", 3072)).items():
+                out[f"adapter_{k}_{kk}"] = v
+        for kk, v in rows_digest(f32("prefill_embed.f32", 3072)).items():
+            out[f"prefill_embed_{kk}"] = v
+        se = f32("step_embed.f32", 3072)
+        for kk, v in rows_digest(se, keep=(0, 1, 2, -1)).items():
+            out[f"step_embed_{kk}"] = v
+    out["n_prefills"] = np.array(man.get("prefills", 0))
     # scenario traces (TRACE_* knobs of ref_trace): how many positions each drain returned, and the alternatives table
     dp = os.path.join(trace, "drain.txt")
     if os.path.exists(dp):
@@ -63,4 +67,4 @@ def main(trace, name):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], slim=len(sys.argv) > 3 and sys.argv[3] == "slim")
