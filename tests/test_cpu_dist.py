@@ -70,3 +70,47 @@ def test_shard_plan_properties():
     assert sh.halo_rows(0) == 0 and sh.halo_rows(300) == 300 and sh.halo_rows(22524) == 750
     # 1-hour config: 8 ranks x ~22.5k positions, each far larger than the 750-row window
     assert min(b - a for a, b in sh.plan_shards(180196, 8)) >= 22520
+
+
+def _halo_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import vbload
+    sh = vbload.load_submodule("sharded")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = 4 * 900 * world + 8                                     # ~3600 positions per rank: more than one 750-row window
+    shards = sh.plan_shards(P, world)
+    p0, p1 = shards[rank]
+    M, h = p1 - p0, sh.halo_rows(p0)
+    # K row of global position g is filled with g, V with -g; halo rows start as garbage
+    own = torch.arange(p0, p1, dtype=torch.float32)[:, None].expand(M, 8).contiguous()
+    kb = torch.full((h + M, 8), 12345.0); vv = torch.full((h + M, 8), 12345.0)
+    kb[h:] = own; vv[h:] = -own
+    for _ in range(2):                                           # two "layers": the exchange is repeatable
+        sh.exchange_halo(dist, rank, world, shards, kb, vv, h, M)
+    a_r = torch.zeros((max((b - a) // 4 for a, b in shards), 4))
+    a_r[:M // 4] = torch.arange(p0 // 4, p1 // 4, dtype=torch.float32)[:, None]
+    adapter = sh.gather_adapter(dist, world, shards, a_r)
+    out[rank] = (kb[:, 0].tolist(), vv[:, 0].tolist(), adapter[:, 0].tolist(), p0, p1, h)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_and_adapter_gather_three_ranks():
+    """The sharded encoder's only data movement, on CPU tensors over gloo: after the exchange every rank's halo area holds
+    exactly the 750 positions that precede its shard, and the gathered adapter rows are complete and in order."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    world = 3
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_halo_worker, args=(world, port, out), nprocs=world, join=True)
+    total_tokens = None
+    for r in range(world):
+        k, v, adapter, p0, p1, h = out[r]
+        assert h == (0 if r == 0 else 750)
+        assert k == [float(g) for g in range(p0 - h, p1)]
+        assert v == [-float(g) for g in range(p0 - h, p1)]
+        total_tokens = out[world - 1][4] // 4
+        assert adapter == [float(t) for t in range(total_tokens)]

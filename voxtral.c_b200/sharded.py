@@ -33,6 +33,31 @@ def halo_rows(start: int) -> int:
     return min(ENC_WINDOW, start)
 
 
+def exchange_halo(dist, rank, world, shards, kb, vv, h, M):
+    """One layer's exchange: rank r's last halo_rows(start of r+1) K/V rows -> rows [0, h) of rank r+1's buffers.
+    kb / vv: [h + M, 2048] torch tensors (any device the process group supports); rows [h, h+M) are this rank's own."""
+    if world <= 1:
+        return
+    ops = []
+    if rank + 1 < world:
+        nxt = halo_rows(shards[rank + 1][0])
+        ops += [dist.P2POp(dist.isend, kb[h + M - nxt:h + M], rank + 1), dist.P2POp(dist.isend, vv[h + M - nxt:h + M], rank + 1)]
+    if rank > 0:
+        ops += [dist.P2POp(dist.irecv, kb[0:h], rank - 1), dist.P2POp(dist.irecv, vv[0:h], rank - 1)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
+def gather_adapter(dist, world, shards, a_r):
+    """All ranks' adapter rows, in position order.  a_r: [T_max, 3072], rows beyond this rank's own count are padding."""
+    import torch
+    if world <= 1:
+        return a_r[:(shards[0][1] - shards[0][0]) // 4].contiguous()
+    parts = [torch.empty_like(a_r) for _ in range(world)]
+    dist.all_gather(parts, a_r)
+    return torch.cat([parts[r][:(shards[r][1] - shards[r][0]) // 4] for r in range(world)], dim=0).contiguous()
+
+
 def stream_mel_device(vb, eng, pcm, delay_tokens=6):
     """mel frames exactly as the stream path sees a complete recording (left pad, flush padding, finish)."""
     L = vb.lib()
@@ -76,29 +101,16 @@ def sharded_encode(vb, eng, pcm, dist, rank, world):
         L.vox_cuda_encoder_layer_qkv(ctx, layer, x.data_ptr(), M, p0, kb.data_ptr(), vv.data_ptr(), h)
         L.vox_cuda_sync(ctx)
         if world > 1:
-            ops = []
-            if rank + 1 < world:
-                nxt = halo_rows(shards[rank + 1][0])
-                ops += [dist.P2POp(dist.isend, kb[h + M - nxt:h + M], rank + 1), dist.P2POp(dist.isend, vv[h + M - nxt:h + M], rank + 1)]
-            if rank > 0:
-                ops += [dist.P2POp(dist.irecv, kb[0:h], rank - 1), dist.P2POp(dist.irecv, vv[0:h], rank - 1)]
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            exchange_halo(dist, rank, world, shards, kb, vv, h, M)
             torch.cuda.synchronize()
         L.vox_cuda_encoder_layer_rest(ctx, layer, x.data_ptr(), M, kb.data_ptr(), vv.data_ptr(), h)
         L.vox_cuda_sync(ctx)
     L.vox_cuda_encoder_final_norm(ctx, x.data_ptr(), M)
-    T_r = M // 4
     T_max = max((b - a) // 4 for a, b in shards)
     a_r = torch.zeros((T_max, 3072), dtype=torch.float32, device=dev)
     L.vox_cuda_adapter(ctx, x.data_ptr(), M, a_r.data_ptr())
     L.vox_cuda_sync(ctx)
-    if world > 1:
-        parts = [torch.empty_like(a_r) for _ in range(world)]
-        dist.all_gather(parts, a_r)
-        adapter = torch.cat([parts[r][:(shards[r][1] - shards[r][0]) // 4] for r in range(world)], dim=0).contiguous()
-    else:
-        adapter = a_r[:T_r].contiguous()
+    adapter = gather_adapter(dist, world, shards, a_r)
     e1.record(); torch.cuda.synchronize()
     t_all["encode_ms"] = e0.elapsed_time(e1)
     t_all["positions"] = P
