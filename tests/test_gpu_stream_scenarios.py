@@ -116,7 +116,6 @@ def test_continuous_mode_kv_restart_matches_reference(engine):
     check_against(g, ids, b"".join(pieces))
 
 
-@pytest.mark.skipif(not os.environ.get("VOX_TEST_PENDING"), reason="written while no GPU slot was free; not yet run on a B200")
 def test_processing_interval_gating_matches_reference(engine):
     """0.25-s feeds with vox_set_processing_interval(0.5 s): the encoder only runs once 50 new mel frames are buffered (S4,
     voxtral.c:793-795,1617-1623), so which feed releases how many positions is part of the contract."""
@@ -136,7 +135,6 @@ def test_processing_interval_gating_matches_reference(engine):
     check_against(g, ids, b"".join(pieces))
 
 
-@pytest.mark.skipif(not os.environ.get("VOX_TEST_PENDING"), reason="written while no GPU slot was free; not yet run on a B200")
 @pytest.mark.parametrize("name,chunk", [("synth_s2p03_oneshot", None), ("synth_s2p03_chunk7001", 7001)])
 def test_ragged_length_matches_reference(engine, name, chunk):
     """32 480 samples (not a multiple of the 1280-sample token: the flush pads 800 alignment zeros first, S2), fed at once
