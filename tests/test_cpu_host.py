@@ -268,3 +268,23 @@ def test_mic_stubs_behave_like_the_reference_off_macos(vb, ref):
         assert L.vox_mic_start() == -1
         assert L.vox_mic_read(buf, 16) == 0 and L.vox_mic_read_available() == 0
         L.vox_mic_stop()
+
+
+def test_scenario_goldens_are_consistent():
+    """Every reference trace under tests/golden/: greedy id == top-1 of the traced logits, top-8 sorted, drain counts add up to
+    the number of text tokens, and the scenario-specific facts the GPU tests rely on."""
+    import glob
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+    assert {"synth_s2_oneshot", "synth_s2_chunk1s", "synth_s2_delay240", "synth_s2_flush", "synth_s2_alt3", "synth_s2_interval05",
+            "synth_s2p03_oneshot", "synth_s2p03_chunk7001", "synth_s172_continuous"} <= set(names)
+    for name in names:
+        g = golden(name)
+        assert np.array_equal(g["tokens"], g["top_idx"][:, 0]), name
+        assert (np.diff(g["top_val"], axis=1) <= 0).all(), name
+        if "drain_n" in g.files:
+            n_text = int(np.sum(g["tokens"] >= 1000))            # control ids (< 1000) never reach the queue
+            assert int(g["drain_n"].sum()) <= n_text and int(g["drain_n"].sum()) >= n_text - 8, name   # invalid (empty) pieces are dropped too
+    assert len(golden("synth_s2_flush")["tokens"]) == 53 and list(golden("synth_s2_flush")["drain_n"]) == [0, 6, 17, 0, 0, 30]
+    assert int(golden("synth_s172_continuous")["n_prefills"]) == 2 and len(golden("synth_s172_continuous")["tokens"]) == 2154
+    assert golden("synth_s2_alt3")["alt"].tobytes().count(b"\n") == 36
+    assert int(golden("synth_s2p03_oneshot")["samples"]) % 1280 == 480
