@@ -12,6 +12,8 @@
  *   - tests/test_cpu_oracle.py runs every function below against the SAME function of the unmodified reference
  *     compiled by oracle/Makefile into oracle/_ref/libvoxref.so, on seeded inputs (bit-exact where the
  *     reference is plain f32 arithmetic, 1e-6 relative where it is -ffast-math / OpenBLAS);
+ *   - the decoder step (orc_decoder_layer_step + norm + logits + argmax) has no same-shaped reference function; it is pinned
+ *     at the model's real dimensions against vox_decoder_forward on a hand-filled vox_ctx_t (tests/c/pin_decoder_step.c);
  *   - the streaming mel restatement is additionally checked against the mel checksums the survey recorded
  *     from the reference on samples/jfk.wav when that file is available.
  * The reference ships no numeric golden vectors of its own; model-level parity

@@ -170,3 +170,22 @@ def test_counts_and_time_conditioning(orc, ref):
         assert (a.value, b.value, c.value, d.value) == want       # SURVEY.md section 8 table + golden synth_s2
     x = np.array([0.5, 3.0, 3.0, -1.0], np.float32)
     assert orc.orc_argmax(P(x), 4) == 1                            # first maximum wins
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference headers (build container only)")
+def test_decoder_step_restatement_matches_reference_forward(orc, ref, tmp_path):
+    """orc_decoder_layer_step x 26 + final norm + tied-embedding logits + argmax vs the reference's own vox_decoder_forward at
+    the real dimensions, three consecutive positions (tests/c/pin_decoder_step.c fills a public vox_ctx_t by hand).  This is
+    the restatement tests/test_gpu_kv_ring_wrap.py uses as its checker."""
+    exe = str(tmp_path / "pin_dec")
+    odir, rdir = os.path.join(ROOT, "oracle", "_build"), os.path.join(ROOT, "oracle", "_ref")
+    subprocess.check_call(["gcc", "-O2", "-I/root/reference", "-I" + os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "c", "pin_decoder_step.c"),
+                           "-o", exe, "-L" + rdir, "-lvoxref", "-L" + odir, "-loracle", "-Wl,-rpath," + rdir, "-Wl,-rpath," + odir, "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr[-500:]
+    lines = [l.split() for l in r.stdout.splitlines() if l.startswith("step")]
+    assert len(lines) == 3
+    for l in lines:
+        diff, scale, same = float(l[3]), float(l[5]), int(l[7])
+        assert same == 1 and diff < 5e-6 * scale * 2          # measured 2.3e-5 on logits of scale 8: -ffast-math summation order
