@@ -14,6 +14,8 @@
  *     reference is plain f32 arithmetic, 1e-6 relative where it is -ffast-math / OpenBLAS);
  *   - the decoder step (orc_decoder_layer_step + norm + logits + argmax) has no same-shaped reference function; it is pinned
  *     at the model's real dimensions against vox_decoder_forward on a hand-filled vox_ctx_t (tests/c/pin_decoder_step.c);
+ *     likewise orc_encoder_layer / orc_adapter against vox_encoder_forward_incremental (two calls, cache carry) and
+ *     vox_adapter_forward (tests/c/pin_encoder_adapter.c);
  *   - the streaming mel restatement is additionally checked against the mel checksums the survey recorded
  *     from the reference on samples/jfk.wav when that file is available.
  * The reference ships no numeric golden vectors of its own; model-level parity
@@ -299,6 +301,53 @@ void orc_decoder_layer_step(float *x, const orc_dec_layer *L, float *kc, float *
     orc_linear_bf16(proj, g, L->w2, NULL, 1, hidden, dim);
     orc_add(x, proj, dim);
     free(xn); free(q); free(att); free(proj); free(g); free(u); free(fr);
+}
+
+/* ---- E2 body at arbitrary dimensions: m new positions through one encoder layer against an explicit K/V cache
+ *      (voxtral_encoder.c:519-619).  kc/vc: [max_rows, n_heads*hd] holding cache_len rows already; the new rows are appended.
+ *      first_pos = logical position of x[0] (RoPE); attention uses physical indices, window-limited (K4).
+ *      Biases: q, v, wo and w2 have one, k / w1 / w3 do not (voxtral.h:56-81). ---- */
+void orc_encoder_layer(float *x, int m, const orc_enc_layer *L, float *kc, float *vc, int cache_len, int first_pos,
+                       int dim, int n_heads, int hd, int hidden, int window, float theta, float eps) {
+    const int qd = n_heads * hd;
+    float *xn = malloc(sizeof(float) * (size_t)m * dim), *q = malloc(sizeof(float) * (size_t)m * qd);
+    float *att = malloc(sizeof(float) * (size_t)m * qd), *proj = malloc(sizeof(float) * (size_t)m * dim);
+    float *g = malloc(sizeof(float) * (size_t)m * hidden), *u = malloc(sizeof(float) * (size_t)m * hidden);
+    float *fr = malloc(sizeof(float) * (size_t)m * hd);
+    int *pos = malloc(sizeof(int) * (size_t)m);
+    float *knew = kc + (size_t)cache_len * qd, *vnew = vc + (size_t)cache_len * qd;
+    for (int i = 0; i < m; i++) pos[i] = first_pos + i;
+    orc_rope_freqs(fr, pos, m, hd, theta);
+    /* attention block */
+    orc_rms_norm(xn, x, L->attn_norm, m, dim, eps);
+    orc_linear_bf16(q, xn, L->wq, L->bq, m, dim, qd);
+    orc_linear_bf16(knew, xn, L->wk, NULL, m, dim, qd);
+    orc_linear_bf16(vnew, xn, L->wv, L->bv, m, dim, qd);
+    orc_apply_rope(q, fr, m, n_heads, hd);
+    orc_apply_rope(knew, fr, m, n_heads, hd);
+    orc_causal_attention(att, q, kc, vc, m, cache_len + m, n_heads, n_heads, hd, 1.0f / sqrtf((float)hd), window, cache_len);
+    orc_linear_bf16(proj, att, L->wo, L->bo, m, qd, dim);
+    orc_add(x, proj, m * dim);
+    /* gated feed-forward block */
+    orc_rms_norm(xn, x, L->ffn_norm, m, dim, eps);
+    orc_linear_bf16(g, xn, L->w1, NULL, m, dim, hidden);
+    orc_silu(g, m * hidden);
+    orc_linear_bf16(u, xn, L->w3, NULL, m, dim, hidden);
+    orc_mul(g, u, m * hidden);
+    orc_linear_bf16(proj, g, L->w2, L->b2, m, hidden, dim);
+    orc_add(x, proj, m * dim);
+    free(xn); free(q); free(att); free(proj); free(g); free(u); free(fr); free(pos);
+}
+
+/* ---- E5: adapter (voxtral_encoder.c:642-674): four consecutive encoder rows are one input row (a free reshape of row-major
+ *      data), Linear(4*enc_dim -> dec_dim), GELU, Linear(dec_dim -> dec_dim), no biases.  rows must be a multiple of 4. ---- */
+void orc_adapter(float *out, const float *enc, int rows, const uint16_t *w0, const uint16_t *w1, int enc_dim, int dec_dim) {
+    const int t = rows / 4;
+    float *h = malloc(sizeof(float) * (size_t)t * dec_dim);
+    orc_linear_bf16(h, enc, w0, NULL, t, 4 * enc_dim, dec_dim);
+    orc_gelu(h, t * dec_dim);
+    orc_linear_bf16(out, h, w1, NULL, t, dec_dim, dec_dim);
+    free(h);
 }
 
 /* ---- stream bookkeeping restated as pure integer functions ---- */

@@ -32,6 +32,14 @@ typedef struct {
 } orc_dec_layer;
 void orc_decoder_layer_step(float *x, const orc_dec_layer *L, float *kc, float *vc, int pos, int logical_pos,
                             int dim, int n_heads, int n_kv, int hd, int hidden, int window, float theta, float eps);
+typedef struct {
+    const uint16_t *wq, *wk, *wv, *wo, *w1, *w2, *w3;   /* bf16, row-major [out,in] */
+    const float *bq, *bv, *bo, *b2;                     /* wk, w1, w3 have no bias */
+    const float *attn_norm, *ffn_norm;
+} orc_enc_layer;
+void orc_encoder_layer(float *x, int m, const orc_enc_layer *L, float *kc, float *vc, int cache_len, int first_pos,
+                       int dim, int n_heads, int hd, int hidden, int window, float theta, float eps);
+void orc_adapter(float *out, const float *enc, int rows, const uint16_t *w0, const uint16_t *w1, int enc_dim, int dec_dim);
 void orc_stream_counts(int n_samples, int delay_tokens, int *mel_frames, int *enc_positions, int *adapter_tokens,
                        int *decoder_steps);
 #endif

@@ -189,3 +189,21 @@ def test_decoder_step_restatement_matches_reference_forward(orc, ref, tmp_path):
     for l in lines:
         diff, scale, same = float(l[3]), float(l[5]), int(l[7])
         assert same == 1 and diff < 5e-6 * scale * 2          # measured 2.3e-5 on logits of scale 8: -ffast-math summation order
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference headers (build container only)")
+def test_encoder_layer_and_adapter_restatements_match_reference(orc, ref, tmp_path):
+    """orc_encoder_layer x 32 + final norm vs vox_encoder_forward_incremental over two calls (7 then 5 rows: K/V cache carry,
+    logical RoPE positions), and orc_adapter vs vox_adapter_forward, at the real dimensions (tests/c/pin_encoder_adapter.c)."""
+    exe = str(tmp_path / "pin_enc")
+    odir, rdir = os.path.join(ROOT, "oracle", "_build"), os.path.join(ROOT, "oracle", "_ref")
+    subprocess.check_call(["gcc", "-O2", "-I/root/reference", "-I" + os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "c", "pin_encoder_adapter.c"),
+                           "-o", exe, "-L" + rdir, "-lvoxref", "-L" + odir, "-loracle", "-Wl,-rpath," + rdir, "-Wl,-rpath," + odir, "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr[-500:]
+    checks = {l.split()[0]: (float(l.split()[2]), float(l.split()[4])) for l in r.stdout.splitlines() if "max_abs_diff" in l}
+    assert set(checks) == {"encoder_call_1", "encoder_call_2", "adapter"}
+    for name, (diff, scale) in checks.items():
+        assert diff < 2e-5 * max(scale, 1.0), name             # measured 5e-6..6e-6: OpenBLAS / -ffast-math summation order
+    assert "enc_cache_len 12" in r.stdout
