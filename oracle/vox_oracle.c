@@ -339,6 +339,24 @@ void orc_encoder_layer(float *x, int m, const orc_enc_layer *L, float *kc, float
     free(xn); free(q); free(att); free(proj); free(g); free(u); free(fr); free(pos);
 }
 
+/* ---- E1/E4, whole-sequence form (voxtral_encoder.c:146-185): mel [frames, bins] -> conv k3 s1 -> GELU -> conv k3 s2 -> GELU ->
+ *      [ceil(frames/2), dim], both convs causal (K5 orc_causal_conv1d works channel-major, hence the two layout changes).
+ *      The streaming form with its tails and odd-row residual (voxtral.c:537-715) is orchestration around the same arithmetic
+ *      and is pinned at stream level by the traces under tests/golden/. ---- */
+void orc_conv_stem(float *out, const float *mel, int frames, const float *w0, const float *b0, const float *w1, const float *b1,
+                   int mel_bins, int dim) {
+    const int l0 = orc_causal_conv1d_out_len(frames, 3, 1), l1 = orc_causal_conv1d_out_len(l0, 3, 2);
+    float *cm = malloc(sizeof(float) * (size_t)mel_bins * frames);
+    float *c0 = malloc(sizeof(float) * (size_t)dim * l0), *c1 = malloc(sizeof(float) * (size_t)dim * l1);
+    for (int f = 0; f < frames; f++) for (int b = 0; b < mel_bins; b++) cm[(size_t)b * frames + f] = mel[(size_t)f * mel_bins + b];
+    orc_causal_conv1d(c0, cm, w0, b0, mel_bins, dim, frames, 3, 1);
+    orc_gelu(c0, dim * l0);
+    orc_causal_conv1d(c1, c0, w1, b1, dim, dim, l0, 3, 2);
+    orc_gelu(c1, dim * l1);
+    for (int p = 0; p < l1; p++) for (int d = 0; d < dim; d++) out[(size_t)p * dim + d] = c1[(size_t)d * l1 + p];
+    free(cm); free(c0); free(c1);
+}
+
 /* ---- E5: adapter (voxtral_encoder.c:642-674): four consecutive encoder rows are one input row (a free reshape of row-major
  *      data), Linear(4*enc_dim -> dec_dim), GELU, Linear(dec_dim -> dec_dim), no biases.  rows must be a multiple of 4. ---- */
 void orc_adapter(float *out, const float *enc, int rows, const uint16_t *w0, const uint16_t *w1, int enc_dim, int dec_dim) {

@@ -39,6 +39,8 @@ typedef struct {
 } orc_enc_layer;
 void orc_encoder_layer(float *x, int m, const orc_enc_layer *L, float *kc, float *vc, int cache_len, int first_pos,
                        int dim, int n_heads, int hd, int hidden, int window, float theta, float eps);
+void orc_conv_stem(float *out, const float *mel, int frames, const float *w0, const float *b0, const float *w1, const float *b1,
+                   int mel_bins, int dim);
 void orc_adapter(float *out, const float *enc, int rows, const uint16_t *w0, const uint16_t *w1, int enc_dim, int dec_dim);
 void orc_stream_counts(int n_samples, int delay_tokens, int *mel_frames, int *enc_positions, int *adapter_tokens,
                        int *decoder_steps);

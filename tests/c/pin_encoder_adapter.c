@@ -2,7 +2,8 @@
  * pin_encoder_adapter.c -- pins oracle/vox_oracle.c:orc_encoder_layer (x32 + final norm) and orc_adapter against the UNMODIFIED
  * reference's vox_encoder_forward_incremental (voxtral_encoder.c:452-636) and vox_adapter_forward (:642-674) at the model's real
  * dimensions, on a hand-filled public vox_ctx_t (all layers share seven random bf16 matrices, each has its own norms and biases).
- * Two incremental calls (7 rows, then 5) exercise the encoder K/V cache carry and the logical RoPE positions.
+ * vox_encoder_forward on 22 mel frames pins the conv stem (orc_conv_stem) + a cold-cache pass; two incremental calls (7 rows,
+ * then 5) exercise the encoder K/V cache carry and the logical RoPE positions.
  * Built and run by tests/test_cpu_oracle.py; prints one "max_abs_diff <x> scale <y>" line per check, exit code 1 on mismatch.
  */
 #include "voxtral.h"
@@ -57,10 +58,33 @@ int main(void) {
     ctx->adapter.linear0_weight_bf16 = rand_bf16(VOX_DEC_DIM, 4 * (size_t)D, sqrtf(3.0f / (4 * D)));
     ctx->adapter.linear1_weight_bf16 = rand_bf16(VOX_DEC_DIM, VOX_DEC_DIM, sqrtf(3.0f / VOX_DEC_DIM));
 
+    ctx->encoder.conv0_weight = rand_f32((size_t)D * VOX_MEL_BINS * 3, 0.f, sqrtf(3.0f / (VOX_MEL_BINS * 3)));
+    ctx->encoder.conv0_bias = rand_f32(D, 0.f, 0.05f);
+    ctx->encoder.conv1_weight = rand_f32((size_t)D * D * 3, 0.f, sqrtf(3.0f / (D * 3)));
+    ctx->encoder.conv1_bias = rand_f32(D, 0.f, 0.05f);
+
+    int bad = 0;
+    {   /* E4: whole-sequence encoder = conv stem + 32 layers from an empty cache + final norm */
+        const int frames = 22, pos = 11;
+        float *mel = rand_f32((size_t)frames * VOX_MEL_BINS, 0.2f, 0.8f);
+        int n = 0;
+        float *y_ref = vox_encoder_forward(ctx, mel, frames, &n);
+        if (!y_ref || n != pos) return 5;
+        float *x = malloc((size_t)pos * D * 4);
+        orc_conv_stem(x, mel, frames, ctx->encoder.conv0_weight, ctx->encoder.conv0_bias, ctx->encoder.conv1_weight, ctx->encoder.conv1_bias,
+                      VOX_MEL_BINS, D);
+        float *k1 = calloc((size_t)pos * QD, 4), *v1 = calloc((size_t)pos * QD, 4);
+        for (int l = 0; l < VOX_ENC_LAYERS; l++)
+            orc_encoder_layer(x, pos, &L[l], k1, v1, 0, 0, D, VOX_ENC_HEADS, VOX_ENC_HEAD_DIM, H, VOX_ENC_WINDOW, VOX_ROPE_THETA, VOX_ENC_NORM_EPS);
+        orc_rms_norm(x, x, ctx->encoder.norm, pos, D, VOX_ENC_NORM_EPS);
+        bad |= report("encoder_full", x, y_ref, (size_t)pos * D);
+        free(x); free(k1); free(v1); free(y_ref); free(mel);
+    }
+
     const int calls[2] = { 7, 5 }, max_rows = 16;
     float *kc = calloc((size_t)VOX_ENC_LAYERS * max_rows * QD, 4), *vc = calloc((size_t)VOX_ENC_LAYERS * max_rows * QD, 4);
     float *all_ref = malloc((size_t)12 * D * 4);
-    int bad = 0, done = 0;
+    int done = 0;
     for (int c = 0; c < 2; c++) {
         const int m = calls[c];
         float *xin = rand_f32((size_t)m * D, 0.f, 1.2f);

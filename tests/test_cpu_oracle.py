@@ -203,7 +203,7 @@ def test_encoder_layer_and_adapter_restatements_match_reference(orc, ref, tmp_pa
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr[-500:]
     checks = {l.split()[0]: (float(l.split()[2]), float(l.split()[4])) for l in r.stdout.splitlines() if "max_abs_diff" in l}
-    assert set(checks) == {"encoder_call_1", "encoder_call_2", "adapter"}
+    assert set(checks) == {"encoder_full", "encoder_call_1", "encoder_call_2", "adapter"}
     for name, (diff, scale) in checks.items():
         assert diff < 2e-5 * max(scale, 1.0), name             # measured 5e-6..6e-6: OpenBLAS / -ffast-math summation order
     assert "enc_cache_len 12" in r.stdout
