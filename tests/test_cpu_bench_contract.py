@@ -1,0 +1,45 @@
+"""bench.py's host-side arithmetic, without a GPU: the unit counts it reports per workload are the ones the reference produces
+(restated in oracle/vox_oracle.c:orc_stream_counts and checked against the compiled reference in
+tests/test_cpu_oracle.py), and the command line keeps the driver's contract."""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_expected_counts_match_the_survey_table_and_the_oracle():
+    b = _bench()
+    table = {176000: (1496, 748, 187, 149), 480000: (3392, 1696, 424, 386), 9600000: (60392, 30196, 7549, 7511),
+             57600000: (360392, 180196, 45049, 45011)}
+    for n, want in table.items():
+        assert b.expected_counts(n) == want
+    so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
+    orc = C.CDLL(so)
+    for n in (1, 1279, 1280, 31337, 32480, 176000, 480001, 9600000):
+        f, p, t, d = (C.c_int() for _ in range(4))
+        orc.orc_stream_counts(n, 6, C.byref(f), C.byref(p), C.byref(t), C.byref(d))
+        assert b.expected_counts(n) == (f.value, p.value, t.value, d.value), n
+
+
+def test_command_line_contract():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0
+    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+        assert flag in r.stdout
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for key in ('"metric"', '"value"', '"unit"', '"n_gpus"', '"steps"', '"warmup"', '"ms_per_step"', '"higher_is_better"', '"scaling"',
+                '"vs_baseline"', '"dtype"', '"data"', '"config"', '"e2e"', '"gpu_launches"', '"clocks"', '"roofline"', '"cpu_baseline"',
+                '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"traffic"', '"frac"', '"peak"', '"achieved"', '"bound"'):
+        assert key in src, key
