@@ -156,3 +156,16 @@ def test_ragged_length_matches_reference(engine, name, chunk):
     assert counts["adapter_tokens"] == 75 and counts["mel_frames"] == 600
     assert drains == [int(n) for n in g["drain_n"]]
     check_against(g, ids, b"".join(pieces))
+
+
+@pytest.mark.skipif(not os.environ.get("VOX_TEST_PENDING"), reason="fixture generated after the round's GPU budget was spent; not yet run on a B200")
+def test_30s_oneshot_matches_reference(engine):
+    """BASELINE.json configs[1]: one 30 s clip fed at once -- a single encoder call over 1696 positions, i.e. the 750-wide
+    attention band lies inside one call, then 386 decoder steps."""
+    g = golden("synth_s30_oneshot")
+    pcm = read_wav_f32(synth_wav(30))
+    assert pcm.size == int(g["samples"]) == 480000
+    s = engine.stream(); s.feed(pcm); s.finish()
+    text = b"".join(s.get()); ids = s.token_ids().copy(); counts = s.counts(); s.close()
+    assert counts["adapter_tokens"] == 424 and counts["mel_frames"] == 3392
+    check_against(g, ids, text)
