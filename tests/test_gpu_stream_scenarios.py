@@ -169,3 +169,39 @@ def test_30s_oneshot_matches_reference(engine):
     text = b"".join(s.get()); ids = s.token_ids().copy(); counts = s.counts(); s.close()
     assert counts["adapter_tokens"] == 424 and counts["mel_frames"] == 3392
     check_against(g, ids, text)
+
+
+@pytest.mark.skipif(not os.environ.get("VOX_TEST_PENDING"), reason="fixture generated after the round's GPU budget was spent; not yet run on a B200")
+def test_live_feeding_100ms_matches_reference(engine):
+    """main.c's live mode in miniature: 0.1-s feeds with a 0.1-s processing interval -- after the first chunk every encoder call
+    sees about 10 mel frames (5 positions), and tokens leave the queue one or two per feed.  Per-feed counts must match."""
+    g = golden("synth_s2_live01")
+    pcm = read_wav_f32(synth_wav(2))
+    chunk = int(g["feed_chunk"])
+    assert chunk == 1600
+    s = engine.stream()
+    s.set_interval(0.1)
+    drains, pieces = [], []
+    for off in range(0, pcm.size, chunk):
+        s.feed(pcm[off:off + chunk])
+        got = s.get(); drains.append(len(got)); pieces += got
+    s.finish()
+    got = s.get(); drains.append(len(got)); pieces += got
+    ids = s.token_ids().copy(); s.close()
+    assert drains == [int(n) for n in g["drain_n"]]
+    check_against(g, ids, b"".join(pieces))
+
+
+@pytest.mark.skipif(not os.environ.get("VOX_TEST_PENDING"), reason="fixture generated after the round's GPU budget was spent; not yet run on a B200")
+def test_delay_2400ms_matches_reference(engine):
+    """The largest delay the API accepts: 30 delay tokens, a 63-row prompt, 41 tokens of flush padding."""
+    g = golden("synth_s2_delay2400")
+    pcm = read_wav_f32(synth_wav(2))
+    engine.set_delay(2400)
+    try:
+        s = engine.stream(); s.feed(pcm); s.finish()
+        text = b"".join(s.get()); ids = s.token_ids().copy(); counts = s.counts(); s.close()
+    finally:
+        engine.set_delay(480)
+    assert counts["adapter_tokens"] == 98
+    check_against(g, ids, text)
