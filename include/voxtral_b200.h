@@ -380,10 +380,24 @@ typedef struct {
 } vox_cuda_info_t;
 int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out);
 const char *vox_cuda_version(void);
-/* Decode driver: 0 = auto (persistent megakernel when the device supports cooperative launch),
- * 1 = one kernel per phase replayed as a CUDA graph, 2 = persistent megakernel.  Both produce the same
- * tokens; the graph path exists for validation and profiling of individual phases. */
+/* Decode driver: 0 = auto (5 when the device supports it, else 3, else 1), 1 = one kernel per phase replayed as a CUDA
+ * graph (validation, per-phase profiling), 3 = persistent cooperative kernel with direct streaming loads (round 1),
+ * 5 = persistent kernel with a decoupled TMA weight stream, dynamic row chunks and up to 8 activation columns
+ * (vb_decode_v2.cu).  All produce the same tokens. */
 void vox_cuda_set_decode_mode(vox_ctx_t *ctx, int mode);
+
+/* ---- several streams on one GPU sharing one weight pass ----
+ * vox_cuda_ctx_fork: a second context on the parent's weights (own decoder KV ring, encoder tail, scratch; shared bf16
+ * matrices, time conditioning and CUDA stream).  One vox_stream_t per context, as in the reference (voxtral.c:1226-1228).
+ * Call vox_set_delay on the parent before forking; vox_free() the forks before the parent.
+ * vox_cuda_stream_set_deferred(s, 1): vox_stream_feed / flush / finish run mel -> encoder -> adapter only.
+ * vox_cuda_streams_decode(streams, n <= 8): prefill where needed, then ONE persistent kernel advances all decoders together
+ * (a weight element is read once and multiplied into n activation columns) until every stream has consumed its adapter
+ * rows; tokens are queued per stream exactly as vox_stream_feed would have queued them.  Returns the number of tokens
+ * generated, -1 if a stream cannot be batched (continuous mode, alternatives, another device). */
+vox_ctx_t *vox_cuda_ctx_fork(vox_ctx_t *parent);
+void vox_cuda_stream_set_deferred(vox_stream_t *s, int on);
+int  vox_cuda_streams_decode(vox_stream_t **streams, int n);
 
 /* Forget both KV caches (decoder ring positions and encoder tail), like a freshly loaded ctx. */
 void vox_cuda_reset_caches(vox_ctx_t *ctx);

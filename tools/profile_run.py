@@ -1,6 +1,9 @@
 #!/usr/bin/env python3
 """One pass of the pipeline on N seconds of synthetic audio -- the command profiled under ncu.
-   python tools/profile_run.py [seconds] [passes] [graph|mega]"""
+   python tools/profile_run.py [seconds] [passes] [auto|graph|persist|v2] [n_streams]
+With n_streams > 1 the streams run on forked contexts in deferred mode and vox_cuda_streams_decode() advances all decoders
+in one persistent kernel (one weight pass for all of them)."""
+import hashlib
 import os
 import sys
 
@@ -12,19 +15,40 @@ import vbload  # noqa: E402
 
 seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 4.0
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+mode = sys.argv[3] if len(sys.argv) > 3 else "auto"
+n_streams = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 vb = vbload.load()
 model = ensure_synth_model()
 pcm = read_wav_f32(synth_wav(seconds))
 eng = vb.Engine(model)
-if len(sys.argv) > 3:
-    eng.set_decode_mode(sys.argv[3])
+eng.set_decode_mode(mode)
+engines = [eng] + [eng.fork() for _ in range(n_streams - 1)]
+h = lambda ids: hashlib.md5(ids.tobytes()).hexdigest()[:12]
 for _ in range(passes):
-    s = eng.stream()
+    i0 = eng.info()
+    streams = [e.stream() for e in engines]
     eng.timer_start()
-    s.feed(pcm)
-    s.finish()
+    if n_streams == 1:
+        streams[0].feed(pcm)
+        streams[0].finish()
+    else:
+        for s in streams:
+            s.set_deferred(1)
+            s.feed(pcm)
+        vb.streams_decode(streams)
+        for s in streams:
+            s.finish()
+        vb.streams_decode(streams)
     ms = eng.timer_stop_ms()
-    ids = s.token_ids()
-    print(f"{seconds:g}s audio: {len(ids)} decoder steps, {ms:.1f} ms device time, RTF {seconds / (ms / 1e3):.1f}, info {eng.info()}")
-    s.close()
+    i1 = eng.info()
+    ids = [s.token_ids() for s in streams]
+    dsteps = i1["total_decode_steps"] - i0["total_decode_steps"]
+    dms = i1["total_decode_kernel_ms"] - i0["total_decode_kernel_ms"]
+    print(f"{seconds:g}s audio x {n_streams} stream(s), mode {mode}: {len(ids[0])} decoder steps/stream, {ms:.1f} ms device time, "
+          f"aggregate RTF {n_streams * seconds / (ms / 1e3):.1f}, decode {dms / max(dsteps, 1):.3f} ms/step over {dsteps} steps, "
+          f"ids md5 {[h(x) for x in ids]}", flush=True)
+    for s in streams:
+        s.close()
+for e in engines[1:]:
+    e.close()
 eng.close()

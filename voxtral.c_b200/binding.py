@@ -110,6 +110,8 @@ def lib():
         "vox_cuda_timer_start": (None, [vp]), "vox_cuda_timer_stop_ms": (C.c_double, [vp]),
         "vox_cuda_stream_token_ids": (i, [vp, c_int_p, i]),
         "vox_cuda_stream_counts": (i, [vp, c_int_p, c_int_p, c_int_p]),
+        "vox_cuda_ctx_fork": (vp, [vp]), "vox_cuda_stream_set_deferred": (None, [vp, i]),
+        "vox_cuda_streams_decode": (i, [C.POINTER(vp), i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -152,13 +154,20 @@ def take(ptr, shape):
 class Engine:
     """vox_ctx_t wrapper."""
 
-    def __init__(self, model_dir, verbose=0):
+    def __init__(self, model_dir, verbose=0, _ctx=None):
         L = lib()
         C.c_int.in_dll(L, "vox_verbose").value = verbose
-        self.ctx = L.vox_load(model_dir.encode())
+        self.ctx = _ctx if _ctx is not None else L.vox_load(model_dir.encode())
         if not self.ctx:
             raise RuntimeError(f"vox_load({model_dir}) failed (no GPU, or bad checkpoint)")
         self.model_dir = model_dir
+
+    def fork(self):
+        """A second context on the same weights (vox_cuda_ctx_fork); close it before the parent."""
+        c = lib().vox_cuda_ctx_fork(self.ctx)
+        if not c:
+            raise RuntimeError("vox_cuda_ctx_fork failed")
+        return Engine(self.model_dir, _ctx=c)
 
     def close(self):
         if self.ctx:
@@ -192,7 +201,7 @@ class Engine:
         lib().vox_set_delay(self.ctx, int(delay_ms))
 
     def set_decode_mode(self, mode):
-        lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "mega": 2, "persist": 3, "tc": 4}[mode])
+        lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "mega": 2, "persist": 3, "tc": 4, "v2": 5}[mode])
 
     def reset_caches(self):
         lib().vox_cuda_reset_caches(self.ctx)
@@ -220,6 +229,12 @@ class Engine:
         return take(p, (n.value, 3072))
 
 
+def streams_decode(streams):
+    """vox_cuda_streams_decode over Stream objects put in deferred mode: one weight pass for all of them."""
+    arr = (C.c_void_p * len(streams))(*[s.s for s in streams])
+    return lib().vox_cuda_streams_decode(arr, len(streams))
+
+
 class Stream:
     """vox_stream_t wrapper."""
 
@@ -244,6 +259,9 @@ class Stream:
 
     def set_interval(self, seconds):
         lib().vox_set_processing_interval(self.s, seconds)
+
+    def set_deferred(self, on):
+        lib().vox_cuda_stream_set_deferred(self.s, int(on))
 
     def set_continuous(self, on):
         lib().vox_stream_set_continuous(self.s, int(on))

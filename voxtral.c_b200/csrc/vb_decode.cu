@@ -357,7 +357,8 @@ static int decode_driver(VbEngine *e) {
         else if (m && !strcmp(m, "mega")) e->decode_mode = 2;
         else if (m && !strcmp(m, "persist")) e->decode_mode = 3;
         else if (m && !strcmp(m, "tc")) e->decode_mode = 4;
-        else e->decode_mode = vb_decoder_persist_supported(e) ? 3 : 1;
+        else if (m && !strcmp(m, "v2")) e->decode_mode = 5;
+        else e->decode_mode = vb_decoder_v2_supported(e) ? 5 : vb_decoder_persist_supported(e) ? 3 : 1;
     }
     if (e->decode_mode == 2 && !vb_decoder_mega_supported(e)) {   /* also sets the kernel's shared-memory attribute */
         fprintf(stderr, "voxtral_b200: TMA-ring megakernel requested but unavailable on this device\n"); abort();
@@ -367,6 +368,9 @@ static int decode_driver(VbEngine *e) {
     }
     if (e->decode_mode == 4 && !vb_decoder_tc_supported(e)) {
         fprintf(stderr, "voxtral_b200: tensor-core ring decode kernel requested but unavailable on this device\n"); abort();
+    }
+    if (e->decode_mode == 5 && !vb_decoder_v2_supported(e)) {
+        fprintf(stderr, "voxtral_b200: v2 decode kernel requested but unavailable on this device\n"); abort();
     }
     return e->decode_mode;
 }
@@ -385,7 +389,10 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
         if (chunk > max_chunk) chunk = max_chunk;
         if (mega) {
             VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
-            if (driver == 2) vb_decoder_mega_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
+            if (driver == 5) {
+                VbV2Col col = { e, d_adapter, adapter_row + done, chunk, prev_token, pos + done };
+                if (vb_decoder_v2_launch(e, &col, 1, chunk, 0, NULL) != 0) { fprintf(stderr, "voxtral_b200: v2 decode launch failed\n"); abort(); }
+            } else if (driver == 2) vb_decoder_mega_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             else if (driver == 4) vb_decoder_tc_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             else vb_decoder_persist_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             VB_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
@@ -406,10 +413,10 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
             VB_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         }
         VbDecState st;
-        VB_CUDA_OK(cudaMemcpyAsync(&st, e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream));
+        VB_CUDA_OK(cudaMemcpyAsync(&st, driver == 5 ? e->v2.st : e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream));
         cudaError_t serr = cudaStreamSynchronize(e->stream);
         if (serr != cudaSuccess) {
-            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), driver == 1 ? "graph" : driver == 2 ? "tma-ring" : driver == 4 ? "tc-ring" : "persist");
+            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), driver == 1 ? "graph" : driver == 2 ? "tma-ring" : driver == 4 ? "tc-ring" : driver == 5 ? "v2" : "persist");
             abort();
         }
         VB_CUDA_OK(cudaMemcpy(e->h_tokens_pinned, e->d_tokens, (size_t)st.n_out * 4, cudaMemcpyDeviceToHost));

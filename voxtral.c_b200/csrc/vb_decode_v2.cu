@@ -1,0 +1,821 @@
+/*
+ * vb_decode_v2.cu -- persistent decode kernel, second generation: a decoupled weight stream and B activation columns.
+ *
+ * What round 1 measured (profiles/r01_decode.md): the GEMV core streams at 99 % of the HBM peak inside the long logits
+ * phase, but a decode step is 131 dependent phases of 4-20 us and every phase boundary (drain, grid barrier, activation
+ * reload, RMSNorm, ramp) idles HBM for ~5 us: 0.59 of the roofline.  And one stream can never beat one weight pass
+ * (6.86 GB) per 80 ms of audio.  This kernel attacks both:
+ *
+ *   weight stream   one producer warp per CTA walks the WHOLE schedule (step -> layer -> phase) independently of the
+ *                   activations and copies weight rows with cp.async.bulk (TMA, mbarrier complete_tx) into an 8 x 24 KB
+ *                   shared-memory ring.  It never waits for a phase boundary: while the 12 consumer warps sit in a grid
+ *                   barrier, in attention or in an RMSNorm, the next phase's rows keep arriving, and the consumers (which
+ *                   read shared memory several times faster than HBM delivers) catch up afterwards.  The number of bulk
+ *                   copies in flight per SM is capped (a.inflight_max) so that barrier polls and activation reloads
+ *                   do not queue behind megabytes of prefetch -- the effect that cancelled round 1's gains.
+ *   work balance    SMs do not get equal shares of HBM bandwidth (10-15 % spread).  The three large phases (QKV, w1|w3,
+ *                   logits) are therefore handed out dynamically: a chunk = 4 consecutive output rows, taken from a
+ *                   per-phase atomic counter by the producer, three grabs ahead.  Every output row is still computed by
+ *                   exactly one CTA in a fixed order, so results do not depend on who took which chunk.
+ *   B columns       every weight element read from shared memory is multiplied into NB activation columns (template
+ *                   parameter; FFMA2 on column pairs).  A column is an independent stream (own KV ring, position,
+ *                   adapter rows, token feedback) -- several vox_stream_t share one weight pass -- or, in verify mode,
+ *                   consecutive positions of ONE stream (drafted tokens, longest matching prefix accepted).
+ *                   The arithmetic of a column (FMA order, reduction tree) is the same for every NB, so a stream decodes
+ *                   to the same ids alone or batched.
+ *   uniform rows    wo (K=4096) and w2 (K=9216) are walked in 2 / 3 column blocks of 2048 / 3072 with the partial sums
+ *                   kept per row in shared memory, so every phase has 8 activations x NB per thread in registers and the
+ *                   kernel has one GEMV loop.  These two phases keep a static row partition (a row's blocks must meet in
+ *                   one CTA).
+ *
+ * Per-step math and epilogues are those of vb_decode_persist.cu / the reference: voxtral_decoder.c:586-706, loop
+ * voxtral.c:1056-1093.
+ */
+#include "vb_decode_persist_common.cuh"
+#include <string.h>
+
+#define V2_CONS        384                     /* consumer threads: 12 warps, 8 k-columns each for a 3072-wide row */
+#define V2_CW          (V2_CONS / 32)
+#define V2_THREADS     (V2_CONS + 32)          /* + producer warp */
+#define V2_SLOTS       8
+#define V2_SLOT_BYTES  24576                   /* 4 rows of 3072 bf16 */
+#define V2_RC          4                       /* rows per chunk */
+#define V2_MAXB        8
+#define V2_SUBPHASES   (VOX_DEC_LAYERS * 4 + 1)
+#define V2_ATT_FLOATS  (V2_CW * 4 * 132)
+#define V2_PROF_SLOTS  320
+#define V2_MAX_STEPS   2048
+#define V2_NSPLIT_MAX  20
+
+struct V2Col {
+    const float *adapter;                      /* adapter rows of this stream */
+    float *kv_k, *kv_v;                        /* [26][8192][1024] ring of this stream */
+    float *logits;                             /* [131072] */
+    int *tokens;                               /* out: generated ids */
+    int pos0, token0, arow0, n_steps;
+};
+
+struct V2Args {
+    DecParams p;                               /* weights (activation pointers in there are not used) */
+    V2Col col[V2_MAXB];
+    float *x, *q, *attn_out, *gate;            /* [nb][3072], [nb][4096], [nb][4096], [nb][9216] */
+    float *part_m, *part_l, *part_o;           /* [nb][20][32], [nb][20][32], [nb][20][32][128] */
+    unsigned long long *argmax;                /* [grid][V2_MAXB] */
+    unsigned int *bar;                         /* [0] grid barrier, [16..23] attention tickets, [32] error word */
+    unsigned int *ctr;                         /* [n_steps][V2_SUBPHASES] chunk counters of the dynamic phases */
+    VbDecState *st_out;                        /* [nb] */
+    int nb, n_steps, inflight_max, dynamic, verify;
+    long long *prof; int prof_step;
+};
+
+struct V2Smem {
+    uint64_t full[V2_SLOTS], empty[V2_SLOTS];
+    int meta_row0[V2_SLOTS], meta_nrows[V2_SLOTS];
+    float red[2][V2_CW][32];
+    float sred[V2_CW][V2_MAXB];
+    float part[24][V2_MAXB];                    /* per-row partial sums of the column-block phases (wo, w2) */
+    unsigned long long cand[V2_CW][V2_MAXB];
+    /* column state, identical in every CTA */
+    int c_pos[V2_MAXB], c_token[V2_MAXB], c_arow[V2_MAXB], c_done[V2_MAXB], c_nout[V2_MAXB], c_left[V2_MAXB];
+    const float *c_adapter[V2_MAXB]; float *c_kv_k[V2_MAXB], *c_kv_v[V2_MAXB], *c_logits[V2_MAXB]; int *c_tokens[V2_MAXB];
+    volatile int abort_flag, is_last;
+};
+
+__device__ __forceinline__ void v2_bar() { asm volatile("bar.sync 1, %0;" :: "n"(V2_CONS) : "memory"); }
+
+__device__ __forceinline__ void v2_grid_barrier(unsigned int *bar, unsigned int &gen, int *err) {
+    gen++;
+    v2_bar();
+    if (threadIdx.x == 0) {
+        red_release_add(bar, 1u);
+        const unsigned int target = gen * gridDim.x;
+        long long t0 = 0;
+        while (ld_acquire_u32(bar) < target) spin_guard(t0, err, 1);
+    }
+    v2_bar();
+}
+
+/* ------------------------------------------------------------------ the weight schedule */
+struct V2Phase { const uint8_t *W; int row_stride, seg_bytes, col_off, total_rows, dyn; };
+
+/* ph: 0 QKV, 1 WO (2 column blocks), 2 W13, 3 W2 (3 column blocks), 4 LOGITS */
+__device__ __forceinline__ V2Phase v2_phase(const DecParams &p, int layer, int ph, int part) {
+    V2Phase f;
+    switch (ph) {
+    case 0:  f.W = (const uint8_t *)p.wqkv[layer]; f.row_stride = VOX_DEC_DIM * 2; f.seg_bytes = VOX_DEC_DIM * 2; f.col_off = 0;
+             f.total_rows = VB_DEC_QKV; f.dyn = 1; break;
+    case 1:  f.W = (const uint8_t *)p.wo[layer]; f.row_stride = VB_DEC_Q * 2; f.seg_bytes = 4096; f.col_off = part * 4096;
+             f.total_rows = VOX_DEC_DIM; f.dyn = 0; break;
+    case 2:  f.W = (const uint8_t *)p.w13[layer]; f.row_stride = VOX_DEC_DIM * 2; f.seg_bytes = VOX_DEC_DIM * 2; f.col_off = 0;
+             f.total_rows = 2 * VOX_DEC_HIDDEN; f.dyn = 1; break;
+    case 3:  f.W = (const uint8_t *)p.w2[layer]; f.row_stride = VOX_DEC_HIDDEN * 2; f.seg_bytes = VOX_DEC_DIM * 2; f.col_off = part * VOX_DEC_DIM * 2;
+             f.total_rows = VOX_DEC_DIM; f.dyn = 0; break;
+    default: f.W = (const uint8_t *)p.tok_emb; f.row_stride = VOX_DEC_DIM * 2; f.seg_bytes = VOX_DEC_DIM * 2; f.col_off = 0;
+             f.total_rows = VOX_VOCAB_SIZE; f.dyn = 1; break;
+    }
+    return f;
+}
+
+__device__ __forceinline__ void v2_static_rows(int total, int unit, int &r0, int &r1) {
+    const int units = total / unit;
+    r0 = (int)((long long)units * blockIdx.x / gridDim.x) * unit;
+    r1 = (int)((long long)units * (blockIdx.x + 1) / gridDim.x) * unit;
+}
+
+/* ------------------------------------------------------------------ producer */
+struct V2Producer {
+    V2Smem *sm; uint8_t *slots; int *err; uint32_t it, landed; int inflight_max; bool dead;
+    long long n_chunks, t_wait;
+
+    __device__ __forceinline__ bool acquire() {          /* a free slot, and room under the in-flight cap */
+        const int s = (int)(it % V2_SLOTS);
+        const uint32_t par = (it / V2_SLOTS) & 1u;
+        long long t0 = 0;
+        while (!mbar_try_wait(&sm->empty[s], par ^ 1u)) {
+            if (sm->abort_flag) { dead = true; return false; }
+            spin_guard(t0, err, 2);
+        }
+        while (it - landed >= (uint32_t)inflight_max) {
+            const uint32_t j = landed;
+            if (mbar_try_wait(&sm->full[j % V2_SLOTS], (j / V2_SLOTS) & 1u)) landed++;
+            else { if (sm->abort_flag) { dead = true; return false; } spin_guard(t0, err, 5); }
+        }
+        return true;
+    }
+    __device__ __forceinline__ void push_rows(const V2Phase &f, int row0, int nrows) {
+        if (dead || !acquire()) return;
+        const int s = (int)(it % V2_SLOTS);
+        sm->meta_row0[s] = row0; sm->meta_nrows[s] = nrows;
+        uint8_t *dst = slots + (size_t)s * V2_SLOT_BYTES;
+        const uint8_t *src = f.W + (size_t)row0 * f.row_stride + f.col_off;
+        mbar_expect_tx(&sm->full[s], (uint32_t)(nrows * f.seg_bytes));
+        if (f.seg_bytes == f.row_stride) bulk_g2s(dst, src, (uint32_t)(nrows * f.seg_bytes), &sm->full[s]);
+        else for (int r = 0; r < nrows; r++) bulk_g2s(dst + (size_t)r * f.seg_bytes, src + (size_t)r * f.row_stride, (uint32_t)f.seg_bytes, &sm->full[s]);
+        it++; n_chunks++;
+    }
+    __device__ __forceinline__ void push_marker() {      /* "this CTA has no more rows in this phase" */
+        if (dead || !acquire()) return;
+        const int s = (int)(it % V2_SLOTS);
+        sm->meta_row0[s] = 0; sm->meta_nrows[s] = 0;
+        mbar_arrive(&sm->full[s]);
+        it++;
+    }
+    __device__ __noinline__ void run_phase(const V2Phase &f, unsigned int *ctr, int dynamic) {
+        if (f.dyn && dynamic) {
+            const unsigned int n = (unsigned int)(f.total_rows / V2_RC);
+            unsigned int g0 = atomicAdd(ctr, 1u), g1 = atomicAdd(ctr, 1u), g2 = atomicAdd(ctr, 1u);
+            while (g0 < n && !dead) {
+                push_rows(f, (int)g0 * V2_RC, V2_RC);
+                g0 = g1; g1 = g2; g2 = atomicAdd(ctr, 1u);
+            }
+        } else {
+            int r0, r1;
+            v2_static_rows(f.total_rows, f.dyn ? V2_RC : 1, r0, r1);
+            for (int r = r0; r < r1 && !dead; r += V2_RC) push_rows(f, r, min(V2_RC, r1 - r));
+        }
+        push_marker();
+    }
+};
+
+__device__ void v2_producer(V2Smem *sm, uint8_t *slots, const V2Args &a) {
+    V2Producer P;
+    P.sm = sm; P.slots = slots; P.err = (int *)(a.bar + 32); P.it = 0; P.landed = 0; P.inflight_max = a.inflight_max; P.dead = false;
+    P.n_chunks = 0; P.t_wait = 0;
+    for (int step = 0; step < a.n_steps && !P.dead; step++) {
+        unsigned int *ctr = a.ctr + (size_t)step * V2_SUBPHASES;
+        for (int layer = 0; layer < VOX_DEC_LAYERS && !P.dead; layer++) {
+            P.run_phase(v2_phase(a.p, layer, 0, 0), ctr + layer * 4 + 0, a.dynamic);
+            P.run_phase(v2_phase(a.p, layer, 1, 0), nullptr, 0);
+            P.run_phase(v2_phase(a.p, layer, 1, 1), nullptr, 0);
+            P.run_phase(v2_phase(a.p, layer, 2, 0), ctr + layer * 4 + 2, a.dynamic);
+            P.run_phase(v2_phase(a.p, layer, 3, 0), nullptr, 0);
+            P.run_phase(v2_phase(a.p, layer, 3, 1), nullptr, 0);
+            P.run_phase(v2_phase(a.p, layer, 3, 2), nullptr, 0);
+        }
+        P.run_phase(v2_phase(a.p, 0, 4, 0), ctr + VOX_DEC_LAYERS * 4, a.dynamic);
+    }
+    /* every bulk copy that was issued must land before the CTA may exit (shared memory is its target) */
+    while (P.landed < P.it) {
+        long long t0 = 0;
+        const uint32_t j = P.landed;
+        while (!mbar_try_wait(&sm->full[j % V2_SLOTS], (j / V2_SLOTS) & 1u)) spin_guard(t0, P.err, 4);
+        P.landed++;
+    }
+}
+
+/* ------------------------------------------------------------------ consumer: the one GEMV loop */
+template <int R> struct V2Log2;
+template <> struct V2Log2<1>  { static const int v = 0; };
+template <> struct V2Log2<2>  { static const int v = 1; };
+template <> struct V2Log2<4>  { static const int v = 2; };
+template <> struct V2Log2<8>  { static const int v = 3; };
+template <> struct V2Log2<16> { static const int v = 4; };
+template <> struct V2Log2<32> { static const int v = 5; };
+
+/* lane L ends up with the total (over the warp) of v[L >> (5 - log2 R)] */
+template <int R>
+__device__ __forceinline__ float v2_transpose_reduce(float (&v)[R], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = R; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) {
+            float send = upper ? v[i] : v[i + n / 2];
+            float keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int o = (16 >> V2Log2<R>::v); o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+
+/* activation registers: NB columns x 8 k-values.  NB >= 2 keeps column pairs packed for FFMA2. */
+__device__ __forceinline__ unsigned long long v2_pack(float lo, float hi) {
+    unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void v2_unpack(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+template <int NB> struct V2X {
+    static constexpr int NP = NB / 2;
+    unsigned long long v[NP][8];               /* {col 2j, col 2j+1} at k */
+    /* f(b, k) -> value of column b at this thread's k-th element */
+    template <typename F> __device__ __forceinline__ void fill(F f) {
+#pragma unroll
+        for (int j = 0; j < NP; j++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[j][k] = v2_pack(f(2 * j, k), f(2 * j + 1, k));
+    }
+    __device__ __forceinline__ float get(int b, int k) const {
+        float lo, hi; v2_unpack(v[b >> 1][k], lo, hi);
+        return (b & 1) ? hi : lo;
+    }
+};
+template <> struct V2X<1> {
+    float v[8];
+    template <typename F> __device__ __forceinline__ void fill(F f) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = f(0, k);
+    }
+    __device__ __forceinline__ float get(int, int k) const { return v[k]; }
+};
+
+/* acc[b] += w[k] * x[b][k] for the 8 weights of one 16-byte load, k ascending: the reference's order
+ * (voxtral_kernels.c:154-195) in every column, whatever NB is. */
+template <int NB>
+__device__ __forceinline__ void v2_dot8(const uint4 w, const V2X<NB> &x, float (&acc)[NB]) {
+    const float wf[8] = { vb_bf16_lo(w.x), vb_bf16_hi(w.x), vb_bf16_lo(w.y), vb_bf16_hi(w.y),
+                          vb_bf16_lo(w.z), vb_bf16_hi(w.z), vb_bf16_lo(w.w), vb_bf16_hi(w.w) };
+    if constexpr (NB == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[0] = fmaf(wf[k], x.v[k], acc[0]);
+    } else {
+        unsigned long long a2[NB / 2];
+#pragma unroll
+        for (int j = 0; j < NB / 2; j++) asm("mov.b64 %0, {%1,%2};" : "=l"(a2[j]) : "f"(acc[2 * j]), "f"(acc[2 * j + 1]));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            unsigned long long ww;
+            asm("mov.b64 %0, {%1,%1};" : "=l"(ww) : "f"(wf[k]));
+#pragma unroll
+            for (int j = 0; j < NB / 2; j++) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2[j]) : "l"(ww), "l"(x.v[j][k]));
+        }
+#pragma unroll
+        for (int j = 0; j < NB / 2; j++) asm("mov.b64 {%0,%1}, %2;" : "=f"(acc[2 * j]), "=f"(acc[2 * j + 1]) : "l"(a2[j]));
+    }
+}
+
+/* Consume the chunks of one (sub)phase from the ring until the producer's end marker.
+ * NT = threads that own a 16-byte column of the row segment (384 for 3072-wide, 256 for 2048-wide segments).
+ * epi(row, b, value, lane, valid) runs in the last consumer warp, lane = (row - row0) * NB + b. */
+template <int NB, typename Epi>
+__device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uint32_t &it, int seg_bytes, int NT,
+                                           const V2X<NB> &x, int &redbuf, int *err, Epi epi) {
+    constexpr int R = V2_RC * NB;
+    constexpr int LG = V2Log2<R>::v;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool active = t < NT;
+    for (;;) {
+        const int s = (int)(it % V2_SLOTS);
+        const uint32_t par = (it / V2_SLOTS) & 1u;
+        long long t0 = 0;
+        while (!mbar_try_wait(&sm->full[s], par)) spin_guard(t0, err, 3);
+        const int nrows = sm->meta_nrows[s], row0 = sm->meta_row0[s];
+        float acc[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) acc[i] = 0.f;
+        if (nrows > 0 && active) {
+            const uint8_t *base = slots + (size_t)s * V2_SLOT_BYTES + (size_t)t * 16;
+            uint4 w[V2_RC];
+#pragma unroll
+            for (int r = 0; r < V2_RC; r++) w[r] = (r < nrows) ? *reinterpret_cast<const uint4 *>(base + (size_t)r * seg_bytes) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int r = 0; r < V2_RC; r++) {
+                float a[NB];
+#pragma unroll
+                for (int b = 0; b < NB; b++) a[b] = 0.f;
+                v2_dot8<NB>(w[r], x, a);
+#pragma unroll
+                for (int b = 0; b < NB; b++) acc[r * NB + b] = a[b];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->empty[s]);
+        it++;
+        if (nrows == 0) break;
+        const float tot = v2_transpose_reduce<R>(acc, lane);
+        if ((lane & ((32 >> LG) - 1)) == 0) sm->red[redbuf][warp][lane >> (5 - LG)] = tot;
+        v2_bar();
+        if (warp == V2_CW - 1) {
+            float sum = 0.f;
+            if (lane < R) {
+#pragma unroll
+                for (int wv = 0; wv < V2_CW; wv++) sum += sm->red[redbuf][wv][lane];
+            }
+            epi(row0 + lane / NB, lane % NB, sum, lane, lane < R && lane / NB < nrows);
+        }
+        redbuf ^= 1;
+    }
+}
+
+/* ------------------------------------------------------------------ activation loads */
+template <int NB>
+__device__ __forceinline__ void v2_load_x(V2X<NB> &x, const float *src, int col_stride, int NT) {
+    const int t = threadIdx.x;
+    float4 lo[NB], hi[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        lo[b] = make_float4(0.f, 0.f, 0.f, 0.f); hi[b] = lo[b];
+        if (t < NT) {
+            const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)b * col_stride + (size_t)t * 8);
+            lo[b] = __ldcg(p); hi[b] = __ldcg(p + 1);
+        }
+    }
+    x.fill([&](int b, int k) {
+        const float4 q = k < 4 ? lo[b] : hi[b];
+        const int kk = k & 3;
+        return kk == 0 ? q.x : kk == 1 ? q.y : kk == 2 ? q.z : q.w;
+    });
+}
+
+/* RMSNorm of each column over the 3072 values spread across the 384 threads (voxtral_kernels.c:346-363), optional (1+ada) */
+template <int NB>
+__device__ __forceinline__ void v2_rmsnorm(V2X<NB> &x, const float *__restrict__ w, const float *__restrict__ ada, V2Smem *sm) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float ss[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { float v = x.get(b, j); s = fmaf(v, v, s); }
+        ss[b] = vb_warp_sum(s);
+    }
+    v2_bar();
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) sm->sred[warp][b] = ss[b];
+    }
+    v2_bar();
+    float wk[8], ak[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { wk[j] = w[t * 8 + j]; ak[j] = ada ? ada[t * 8 + j] : 0.f; }
+    float rinv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < V2_CW; i++) tot += sm->sred[i][b];
+        rinv[b] = 1.0f / sqrtf(tot / (float)VOX_DEC_DIM + VOX_DEC_NORM_EPS);
+    }
+    V2X<NB> y;
+    y.fill([&](int b, int j) {
+        float v = x.get(b, j) * rinv[b] * wk[j];
+        if (ada) v *= (1.0f + ak[j]);
+        return v;
+    });
+    x = y;
+}
+
+/* ------------------------------------------------------------------ attention */
+/* kv head h is served by the CTAs with (cta & 7) == h; they split the valid ring slots of each column between them.  Inside a
+ * CTA the 12 warps take interleaved slots (the 4 query heads of the kv head share each K/V row read), merge through shared
+ * memory to one partial per query head and column, publish it; the last CTA to arrive for a kv head (atomic ticket) combines. */
+template <int NB>
+__device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float *att_scr, int layer) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kvh = blockIdx.x & 7, si = blockIdx.x >> 3;
+    const int nsplit = (gridDim.x >> 3) + ((int)(gridDim.x & 7) > kvh ? 1 : 0);
+    const float scale = 1.0f / sqrtf((float)HD);
+#pragma unroll 1
+    for (int b = 0; b < NB; b++) {
+        if (sm->c_done[b]) continue;
+        const int pos = sm->c_pos[b];
+        const int n_valid = min(pos + 1, VB_KV_SLOTS);
+        const int s0 = (int)((long long)n_valid * si / nsplit), s1 = (int)((long long)n_valid * (si + 1) / nsplit);
+        float4 qv[4];
+#pragma unroll
+        for (int hq = 0; hq < 4; hq++) qv[hq] = __ldcg(reinterpret_cast<const float4 *>(a.q + (size_t)b * VB_DEC_Q + (kvh * 4 + hq) * HD + lane * 4));
+        float m[4], l[4]; float4 o[4];
+#pragma unroll
+        for (int hq = 0; hq < 4; hq++) { m[hq] = -1e30f; l[hq] = 0.f; o[hq] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        const float *kb = sm->c_kv_k[b] + (size_t)layer * VB_KV_SLOTS * VB_DEC_KV + kvh * HD + lane * 4;
+        const float *vb = sm->c_kv_v[b] + (size_t)layer * VB_KV_SLOTS * VB_DEC_KV + kvh * HD + lane * 4;
+        for (int sb = s0 + warp; sb < s1; sb += 4 * V2_CW) {       /* this warp's slots: sb, sb+12, sb+24, sb+36 */
+            float4 k4[4], v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int s = min(sb + V2_CW * u, s1 - 1);
+                k4[u] = __ldcg(reinterpret_cast<const float4 *>(kb + (size_t)s * VB_DEC_KV));
+                v4[u] = __ldcg(reinterpret_cast<const float4 *>(vb + (size_t)s * VB_DEC_KV));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (sb + V2_CW * u < s1) {
+                    float sc[4];
+#pragma unroll
+                    for (int hq = 0; hq < 4; hq++)
+                        sc[hq] = qv[hq].x * k4[u].x + qv[hq].y * k4[u].y + qv[hq].z * k4[u].z + qv[hq].w * k4[u].w;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                        for (int hq = 0; hq < 4; hq++) sc[hq] += __shfl_xor_sync(0xffffffffu, sc[hq], off);
+#pragma unroll
+                    for (int hq = 0; hq < 4; hq++) {
+                        float sv = sc[hq] * scale;
+                        float mn = fmaxf(m[hq], sv);
+                        float c = expf(m[hq] - mn), pw = expf(sv - mn);
+                        l[hq] = l[hq] * c + pw;
+                        o[hq].x = o[hq].x * c + pw * v4[u].x; o[hq].y = o[hq].y * c + pw * v4[u].y;
+                        o[hq].z = o[hq].z * c + pw * v4[u].z; o[hq].w = o[hq].w * c + pw * v4[u].w;
+                        m[hq] = mn;
+                    }
+                }
+            }
+        }
+        /* merge the 12 warps: scratch[warp][hq] = {m, l, -, -, o[128]} */
+#pragma unroll
+        for (int hq = 0; hq < 4; hq++) {
+            float *dst = att_scr + (size_t)(warp * 4 + hq) * 132;
+            if (lane == 0) { dst[0] = m[hq]; dst[1] = l[hq]; }
+            *reinterpret_cast<float4 *>(dst + 4 + lane * 4) = o[hq];
+        }
+        v2_bar();
+        if (warp < 4) {
+            const int hq = warp;
+            float M = -1e30f;
+#pragma unroll
+            for (int w = 0; w < V2_CW; w++) M = fmaxf(M, att_scr[(size_t)(w * 4 + hq) * 132]);
+            float L = 0.f; float4 O = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < V2_CW; w++) {
+                const float *src = att_scr + (size_t)(w * 4 + hq) * 132;
+                float lw = src[1];
+                if (lw > 0.f) {
+                    float c = expf(src[0] - M);
+                    float4 ow = *reinterpret_cast<const float4 *>(src + 4 + lane * 4);
+                    L = fmaf(c, lw, L);
+                    O.x = fmaf(c, ow.x, O.x); O.y = fmaf(c, ow.y, O.y); O.z = fmaf(c, ow.z, O.z); O.w = fmaf(c, ow.w, O.w);
+                }
+            }
+            const size_t pi = ((size_t)b * V2_NSPLIT_MAX + si) * VOX_DEC_HEADS + (kvh * 4 + hq);
+            if (lane == 0) { a.part_m[pi] = M; a.part_l[pi] = L; }
+            *reinterpret_cast<float4 *>(a.part_o + pi * HD + lane * 4) = O;
+        }
+        v2_bar();
+    }
+    /* ticket: the last CTA of this kv head combines all columns */
+    if (tid == 0) {
+        __threadfence();
+        unsigned int old = atomicAdd(&a.bar[16 + kvh], 1u);
+        int last = (old == (unsigned int)(nsplit - 1));
+        if (last) { a.bar[16 + kvh] = 0u; __threadfence(); }
+        sm->is_last = last;
+    }
+    v2_bar();
+    if (sm->is_last) {
+        for (int pi2 = warp; pi2 < 4 * NB; pi2 += V2_CW) {
+            const int b = pi2 >> 2, h = kvh * 4 + (pi2 & 3);
+            if (sm->c_done[b]) continue;
+            float mi = -1e30f, li = 0.f;
+            if (lane < nsplit) {
+                mi = __ldcg(a.part_m + ((size_t)b * V2_NSPLIT_MAX + lane) * VOX_DEC_HEADS + h);
+                li = __ldcg(a.part_l + ((size_t)b * V2_NSPLIT_MAX + lane) * VOX_DEC_HEADS + h);
+            }
+            float M = mi;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o2));
+            float wi = li > 0.f ? expf(mi - M) : 0.f;
+            float L = vb_warp_sum(wi * li);
+            float4 O = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ov[V2_NSPLIT_MAX];
+#pragma unroll
+            for (int i = 0; i < V2_NSPLIT_MAX; i++)
+                ov[i] = i < nsplit ? __ldcg(reinterpret_cast<const float4 *>(a.part_o + (((size_t)b * V2_NSPLIT_MAX + i) * VOX_DEC_HEADS + h) * HD + lane * 4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < V2_NSPLIT_MAX; i++) {
+                float c = __shfl_sync(0xffffffffu, wi, i);
+                O.x = fmaf(c, ov[i].x, O.x); O.y = fmaf(c, ov[i].y, O.y); O.z = fmaf(c, ov[i].z, O.z); O.w = fmaf(c, ov[i].w, O.w);
+            }
+            float inv = L > 0.f ? 1.0f / L : 0.f;
+            *reinterpret_cast<float4 *>(a.attn_out + (size_t)b * VB_DEC_Q + h * HD + lane * 4) = make_float4(O.x * inv, O.y * inv, O.z * inv, O.w * inv);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ the kernel */
+extern __shared__ __align__(1024) uint8_t v2_smem_raw[];
+
+#define V2PROF() do { if (a.prof && step == a.prof_step && tid == 0 && prof_n < V2_PROF_SLOTS) \
+    a.prof[(size_t)blockIdx.x * V2_PROF_SLOTS + prof_n++] = clock64(); } while (0)
+
+template <int NB>
+__global__ void __maxnreg__(152) k_dec_v2(const __grid_constant__ V2Args a) {
+    uint8_t *slots = v2_smem_raw;
+    float *att_scr = reinterpret_cast<float *>(v2_smem_raw + (size_t)V2_SLOTS * V2_SLOT_BYTES);
+    V2Smem *sm = reinterpret_cast<V2Smem *>(v2_smem_raw + (size_t)V2_SLOTS * V2_SLOT_BYTES + (size_t)V2_ATT_FLOATS * 4);
+    const DecParams &p = a.p;
+    const int tid = threadIdx.x, lane = tid & 31;
+    int *err = (int *)(a.bar + 32);
+
+    if (tid == 0) {
+        for (int i = 0; i < V2_SLOTS; i++) { mbar_init(&sm->full[i], 1); mbar_init(&sm->empty[i], V2_CW); }
+        sm->abort_flag = 0; sm->is_last = 0;
+        for (int b = 0; b < V2_MAXB; b++) {
+            const bool on = b < a.nb && a.col[b].n_steps > 0;
+            sm->c_pos[b] = a.col[b].pos0; sm->c_token[b] = a.col[b].token0; sm->c_arow[b] = a.col[b].arow0;
+            sm->c_done[b] = on ? 0 : 1; sm->c_nout[b] = 0; sm->c_left[b] = on ? a.col[b].n_steps : 0;
+            sm->c_adapter[b] = a.col[b].adapter; sm->c_kv_k[b] = a.col[b].kv_k; sm->c_kv_v[b] = a.col[b].kv_v;
+            sm->c_logits[b] = a.col[b].logits; sm->c_tokens[b] = a.col[b].tokens;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= V2_CONS) {
+        if (tid == V2_CONS) v2_producer(sm, slots, a);
+        return;
+    }
+
+    /* ===================== consumers ===================== */
+    uint32_t it = 0;
+    unsigned int gen = 0;
+    int redbuf = 0, prof_n = 0;
+    int my_r0, my_r1;                                          /* residual-stream rows this CTA owns (static wo / w2 partition) */
+    v2_static_rows(VOX_DEC_DIM, 1, my_r0, my_r1);
+
+    for (int step = 0; step < a.n_steps; step++) {
+        {   /* all columns finished? (identical decision in every CTA) */
+            int live = 0;
+#pragma unroll
+            for (int b = 0; b < NB; b++) live |= !sm->c_done[b];
+            if (!live) break;
+        }
+        /* residual stream rows owned by this CTA: x = adapter[arow] + tok_emb[token] (voxtral.c:1057-1061) */
+        for (int i = tid; i < (my_r1 - my_r0) * NB; i += V2_CONS) {
+            const int b = i % NB, r = my_r0 + i / NB;
+            const float *ar = sm->c_adapter[b] + (size_t)sm->c_arow[b] * VOX_DEC_DIM;
+            const uint16_t *er = p.tok_emb + (size_t)sm->c_token[b] * VOX_DEC_DIM;
+            a.x[(size_t)b * VOX_DEC_DIM + r] = ar[r] + __uint_as_float((uint32_t)er[r] << 16);
+        }
+
+        /* One GEMV loop for all 26 x 7 + 1 weight (sub)phases of the step (a single copy of the hot code in the I-cache):
+         * sub 0 QKV | 1,2 wo column blocks | 3 w1|w3 | 4,5,6 w2 column blocks | 7 logits (after the last layer). */
+        unsigned long long best = 0ull;                                /* logits: the epilogue lane's column is lane % NB throughout */
+#pragma unroll 1
+        for (int idx = 0; idx <= VOX_DEC_LAYERS * 7; idx++) {
+            const int layer = idx / 7;
+            const int sub = layer == VOX_DEC_LAYERS ? 7 : idx - layer * 7;
+            if (sub == 0 || sub == 7) V2PROF();
+            /* ---- this phase's activation columns: 8 values x NB per thread ---- */
+            V2X<NB> x;
+            int seg_bytes = VOX_DEC_DIM * 2, NT = V2_CONS;
+            if (sub == 0 && layer == 0) {
+                x.fill([&](int b, int j) {
+                    const float *ar = sm->c_adapter[b] + (size_t)sm->c_arow[b] * VOX_DEC_DIM + tid * 8;
+                    const uint16_t *er = p.tok_emb + (size_t)sm->c_token[b] * VOX_DEC_DIM + tid * 8;
+                    return ar[j] + __uint_as_float((uint32_t)er[j] << 16);
+                });
+            } else {
+                const float *src = a.x; int stride = VOX_DEC_DIM;
+                if (sub == 1 || sub == 2) { src = a.attn_out + (sub - 1) * 2048; stride = VB_DEC_Q; seg_bytes = 4096; NT = 256; }
+                else if (sub >= 4 && sub <= 6) { src = a.gate + (sub - 4) * VOX_DEC_DIM; stride = VOX_DEC_HIDDEN; }
+                v2_load_x<NB>(x, src, stride, NT);
+            }
+            if (sub == 0 || sub == 3 || sub == 7) {
+                const float *nw = sub == 0 ? p.attn_norm[layer] : sub == 3 ? p.ffn_norm[layer] : p.final_norm;
+                v2_rmsnorm<NB>(x, nw, sub == 3 ? p.ada + (size_t)layer * VOX_DEC_DIM : nullptr, sm);
+            }
+            const float *inv_freq = p.inv_freq;
+            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, err, [&](int row, int b, float v, int, bool valid) {
+                const float other = __shfl_xor_sync(0xffffffffu, v, NB);    /* row ^ 1 of the same column: RoPE pair / (gate, up) pair */
+                if (!valid) return;
+                switch (sub) {
+                case 0: {   /* RoPE -> q, KV ring (voxtral_decoder.c:626-660) */
+                    if (sm->c_done[b]) return;
+                    const int pos = sm->c_pos[b], slot = pos & (VB_KV_SLOTS - 1);
+                    if (row < VB_DEC_Q + VB_DEC_KV) {
+                        const int d = (row & (HD - 1)) >> 1;
+                        float sn, cs;
+                        sincosf((float)pos * inv_freq[d], &sn, &cs);
+                        const float y = (row & 1) ? (other * sn + v * cs) : (v * cs - other * sn);
+                        if (row < VB_DEC_Q) a.q[(size_t)b * VB_DEC_Q + row] = y;
+                        else sm->c_kv_k[b][((size_t)layer * VB_KV_SLOTS + slot) * VB_DEC_KV + row - VB_DEC_Q] = y;
+                    } else sm->c_kv_v[b][((size_t)layer * VB_KV_SLOTS + slot) * VB_DEC_KV + row - VB_DEC_Q - VB_DEC_KV] = v;
+                    break; }
+                case 1: case 4: sm->part[row - my_r0][b] = v; break;
+                case 5: sm->part[row - my_r0][b] += v; break;
+                case 2: case 6: {   /* last column block: residual add */
+                    float *xp = a.x + (size_t)b * VOX_DEC_DIM + row;
+                    *xp = __ldcg(xp) + (sm->part[row - my_r0][b] + v);
+                    break; }
+                case 3: if (!(row & 1)) a.gate[(size_t)b * VOX_DEC_HIDDEN + (row >> 1)] = vb_silu(v) * other; break;   /* voxtral_decoder.c:682-686 */
+                default: {
+                    sm->c_logits[b][row] = v;
+                    const unsigned long long c = pack_cand(v, row);
+                    if (c > best) best = c;
+                    break; }
+                }
+            });
+            if (sub == 0) {
+                V2PROF();
+                v2_grid_barrier(a.bar, gen, err);
+                V2PROF();
+                v2_attention<NB>(a, sm, att_scr, layer);
+                V2PROF();
+                v2_grid_barrier(a.bar, gen, err);
+                V2PROF();
+            } else if (sub == 2 || sub == 3 || sub == 6) {
+                V2PROF();
+                v2_grid_barrier(a.bar, gen, err);
+                if (sub != 6) V2PROF();
+            }
+        }
+        if (tid >= V2_CONS - 32) {                                     /* per-CTA argmax per column */
+#pragma unroll
+            for (int o = 16; o >= NB; o >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                if (other > best) best = other;
+            }
+            if (lane < NB) a.argmax[(size_t)blockIdx.x * V2_MAXB + lane] = best;
+        }
+        V2PROF();
+        v2_grid_barrier(a.bar, gen, err);
+        V2PROF();
+        {   /* global argmax per column: every CTA reduces the per-CTA candidates, so every CTA knows the tokens */
+            unsigned long long best[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                best[b] = tid < (int)gridDim.x ? __ldcg(a.argmax + (size_t)tid * V2_MAXB + b) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    unsigned long long other = __shfl_xor_sync(0xffffffffu, best[b], o);
+                    if (other > best[b]) best[b] = other;
+                }
+            }
+            v2_bar();
+            if (lane == 0) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) sm->cand[tid >> 5][b] = best[b];
+            }
+            v2_bar();
+            if (tid == 0) {
+                for (int b = 0; b < NB; b++) {
+                    if (sm->c_done[b]) continue;
+                    unsigned long long m = 0ull;
+                    for (int w = 0; w < V2_CW; w++) if (sm->cand[w][b] > m) m = sm->cand[w][b];
+                    const int tok = cand_index(m);
+                    if (blockIdx.x == 0) sm->c_tokens[b][sm->c_nout[b]] = tok;
+                    sm->c_nout[b]++; sm->c_token[b] = tok; sm->c_pos[b]++; sm->c_arow[b]++; sm->c_left[b]--;
+                    if (tok == VB_TOKEN_EOS) sm->c_done[b] = 2;
+                    else if (sm->c_left[b] <= 0) sm->c_done[b] = 1;
+                }
+            }
+            v2_bar();
+        }
+        V2PROF();
+    }
+    if (tid == 0) {
+        sm->abort_flag = 1;                                            /* the producer may be ahead of an early exit (EOS) */
+        if (blockIdx.x == 0) {
+            for (int b = 0; b < a.nb; b++) {
+                VbDecState st;
+                st.pos = sm->c_pos[b]; st.token = sm->c_token[b]; st.eos = sm->c_done[b] == 2; st.n_out = sm->c_nout[b];
+                st.adapter_row = sm->c_arow[b]; st.pad[0] = st.pad[1] = st.pad[2] = 0;
+                a.st_out[b] = st;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ host side */
+static size_t v2_smem_bytes() { return (size_t)V2_SLOTS * V2_SLOT_BYTES + (size_t)V2_ATT_FLOATS * 4 + sizeof(V2Smem); }
+
+template <int NB> static cudaError_t v2_prepare() {
+    return cudaFuncSetAttribute((const void *)k_dec_v2<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2_smem_bytes());
+}
+
+extern "C" int vb_decoder_v2_supported(VbEngine *e) {
+    if (e->v2_checked) return e->v2_ok;
+    e->v2_checked = 1; e->v2_ok = 0;
+    int coop = 0, blocks = 0, smem_optin = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+    if (!coop || e->sm_count > 8 * V2_NSPLIT_MAX || (size_t)smem_optin < v2_smem_bytes()) return 0;
+    if (v2_prepare<1>() != cudaSuccess || v2_prepare<2>() != cudaSuccess || v2_prepare<4>() != cudaSuccess || v2_prepare<8>() != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_dec_v2<8>, V2_THREADS, v2_smem_bytes()) != cudaSuccess || blocks < 1) return 0;
+    e->v2_ok = 1;
+    return 1;
+}
+
+static int v2_alloc(VbEngine *e) {
+    if (e->v2.x) return 0;
+    const size_t wb = e->weight_bytes;
+    VbV2Scratch *s = &e->v2;
+    s->x = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * VOX_DEC_DIM * 4);
+    s->q = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * VB_DEC_Q * 4);
+    s->attn_out = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * VB_DEC_Q * 4);
+    s->gate = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * VOX_DEC_HIDDEN * 4);
+    s->part_m = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * V2_NSPLIT_MAX * VOX_DEC_HEADS * 4);
+    s->part_l = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * V2_NSPLIT_MAX * VOX_DEC_HEADS * 4);
+    s->part_o = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * V2_NSPLIT_MAX * VOX_DEC_HEADS * HD * 4);
+    s->argmax = (unsigned long long *)vb_dev_alloc_owned(e, (size_t)e->sm_count * V2_MAXB * 8);
+    s->bar = (unsigned int *)vb_dev_alloc_owned(e, 256);
+    s->ctr = (unsigned int *)vb_dev_alloc_owned(e, (size_t)V2_MAX_STEPS * V2_SUBPHASES * 4);
+    s->st = (VbDecState *)vb_dev_alloc_owned(e, sizeof(VbDecState) * V2_MAXB);
+    s->prof = NULL;
+    e->weight_bytes = wb;
+    return 0;
+}
+
+static void v2_prof_report(VbEngine *e, const V2Args &a) {
+    size_t n = (size_t)e->sm_count * V2_PROF_SLOTS;
+    long long *h = (long long *)malloc(n * 8);
+    if (cudaMemcpyAsync(h, a.prof, n * 8, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess) { free(h); return; }
+    /* stamps per layer: 0 start, 1 qkv, 2 bar, 3 attn, 4 bar, 5 wo, 6 bar, 7 w13, 8 bar, 9 w2, then (bar) next layer's 0 */
+    static const char *names[10] = { "qkv", "bar", "attn", "bar", "wo", "bar", "w13", "bar", "w2", "bar" };
+    const int ctas[3] = { 0, e->sm_count / 2, e->sm_count - 1 };
+    for (int ci = 0; ci < 3; ci++) {
+        long long *t = h + (size_t)ctas[ci] * V2_PROF_SLOTS;
+        double sum[10] = { 0 };
+        for (int l = 1; l < VOX_DEC_LAYERS - 1; l++)
+            for (int k = 0; k < 10; k++) sum[k] += (double)(t[l * 10 + k + 1] - t[l * 10 + k]);
+        fprintf(stderr, "[v2 prof nb=%d] cta %3d cycles/layer:", a.nb, ctas[ci]);
+        double tot = 0;
+        for (int k = 0; k < 10; k++) { fprintf(stderr, " %s=%.0f", names[k], sum[k] / (VOX_DEC_LAYERS - 2)); tot += sum[k]; }
+        fprintf(stderr, " | layer=%.0f | logits=%lld bar=%lld feedback=%lld step=%lld\n", tot / (VOX_DEC_LAYERS - 2),
+                t[26 * 10 + 1] - t[26 * 10], t[26 * 10 + 2] - t[26 * 10 + 1], t[26 * 10 + 3] - t[26 * 10 + 2], t[26 * 10 + 3] - t[0]);
+    }
+    free(h);
+}
+
+/* cols[i].engine's KV ring / logits / token buffers are used for column i; scratch and the launch stream are the leader's. */
+extern "C" int vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb, int n_steps, int verify, VbDecState *st_host) {
+    if (nb < 1 || nb > V2_MAXB || n_steps < 1) return -1;
+    if (n_steps > V2_MAX_STEPS) n_steps = V2_MAX_STEPS;
+    if (!vb_decoder_v2_supported(lead)) return -1;
+    v2_alloc(lead);
+    V2Args a;
+    memset(&a, 0, sizeof a);
+    a.p = vb_make_dec_params(lead, 1);
+    for (int b = 0; b < nb; b++) {
+        VbEngine *e = cols[b].engine;
+        vb_decoder_alloc(e);
+        a.col[b].adapter = cols[b].d_adapter; a.col[b].kv_k = e->d_kv_k; a.col[b].kv_v = e->d_kv_v;
+        a.col[b].logits = e->d_logits; a.col[b].tokens = e->d_tokens;
+        a.col[b].pos0 = cols[b].pos; a.col[b].token0 = cols[b].prev_token; a.col[b].arow0 = cols[b].adapter_row;
+        a.col[b].n_steps = cols[b].n_steps < n_steps ? cols[b].n_steps : n_steps;
+    }
+    for (int b = nb; b < V2_MAXB; b++) { a.col[b] = a.col[0]; a.col[b].n_steps = 0; }
+    VbV2Scratch *s = &lead->v2;
+    a.x = s->x; a.q = s->q; a.attn_out = s->attn_out; a.gate = s->gate;
+    a.part_m = s->part_m; a.part_l = s->part_l; a.part_o = s->part_o; a.argmax = s->argmax;
+    a.bar = s->bar; a.ctr = s->ctr; a.st_out = s->st;
+    a.nb = nb; a.n_steps = n_steps; a.verify = verify;
+    const char *ev;
+    a.inflight_max = (ev = getenv("VOX_CUDA_V2_INFLIGHT")) ? atoi(ev) : 3;
+    if (a.inflight_max < 1) a.inflight_max = 1;
+    if (a.inflight_max > V2_SLOTS) a.inflight_max = V2_SLOTS;
+    a.dynamic = (ev = getenv("VOX_CUDA_V2_DYNAMIC")) ? atoi(ev) : 1;
+    a.prof = NULL; a.prof_step = -1;
+    if ((ev = getenv("VOX_CUDA_V2_PROF")) && n_steps > atoi(ev)) {
+        if (!s->prof) { const size_t wb = lead->weight_bytes; s->prof = (long long *)vb_dev_alloc_owned(lead, (size_t)lead->sm_count * V2_PROF_SLOTS * 8); lead->weight_bytes = wb; }
+        if (cudaMemsetAsync(s->prof, 0, (size_t)lead->sm_count * V2_PROF_SLOTS * 8, lead->stream) != cudaSuccess) return -1;
+        a.prof = s->prof; a.prof_step = atoi(ev);
+    }
+    if (cudaMemsetAsync(s->bar, 0, 256, lead->stream) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(s->ctr, 0, (size_t)n_steps * V2_SUBPHASES * 4, lead->stream) != cudaSuccess) return -1;
+    void *args[] = { &a };
+    const void *fn = nb == 1 ? (const void *)k_dec_v2<1> : nb == 2 ? (const void *)k_dec_v2<2> : nb <= 4 ? (const void *)k_dec_v2<4> : (const void *)k_dec_v2<8>;
+    cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(lead->sm_count), dim3(V2_THREADS), args, v2_smem_bytes(), lead->stream);
+    if (le != cudaSuccess) { fprintf(stderr, "voxtral_b200: v2 decode launch failed: %s\n", cudaGetErrorString(le)); return -1; }
+    lead->launches += 1;
+    if (a.prof) v2_prof_report(lead, a);
+    if (st_host) {
+        if (cudaMemcpyAsync(st_host, s->st, sizeof(VbDecState) * nb, cudaMemcpyDeviceToHost, lead->stream) != cudaSuccess) return -1;
+    }
+    return 0;
+}

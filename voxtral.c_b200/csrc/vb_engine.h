@@ -66,12 +66,22 @@ typedef struct {
     int pad[3];
 } VbDecState;
 
+/* scratch of the batched persistent decode kernel (vb_decode_v2.cu), owned by the engine that launches it */
+typedef struct {
+    float *x, *q, *attn_out, *gate, *part_m, *part_l, *part_o;
+    unsigned long long *argmax;
+    unsigned int *bar, *ctr;
+    VbDecState *st;
+    long long *prof;
+} VbV2Scratch;
+
 typedef struct VbHostMirror { const void *host; size_t bytes; void *dev; } VbHostMirror;
 
 typedef struct VbEngine {
     vox_ctx_t pub;                              /* MUST be first */
 
     int device, sm_count, cc_major, cc_minor;
+    struct VbEngine *parent;                    /* vox_cuda_ctx_fork: weights, host tensors and the CUDA stream belong to the parent */
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
     cudaEvent_t ev_user0, ev_user1;             /* vox_cuda_timer_* */
@@ -108,6 +118,7 @@ typedef struct VbEngine {
     int decode_mode;                            /* 0 = auto, 1 = CUDA-graph phases, 2 = persistent kernel with TMA weight ring, 3 = persistent kernel, direct loads, 4 = persistent kernel, TMA ring + mma.sync consumer */
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
+    VbV2Scratch v2; int v2_checked, v2_ok;
 
     /* ---- M>1 scratch (prefill / encoder / adapter) ---- */
     float *ws[VB_WS_SLOTS]; size_t ws_bytes[VB_WS_SLOTS];         /* grow-on-demand workspaces */
@@ -158,6 +169,11 @@ int  vb_decoder_tc_supported(VbEngine *e);
 int  vb_decoder_tc_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 int  vb_decoder_persist_supported(VbEngine *e);
 int  vb_decoder_persist_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
+
+/* vb_decode_v2.cu: one weight pass for up to 8 columns (independent streams, or drafted positions of one stream) */
+typedef struct { struct VbEngine *engine; const float *d_adapter; int adapter_row, n_steps, prev_token, pos; } VbV2Col;
+int  vb_decoder_v2_supported(VbEngine *e);
+int  vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb, int n_steps, int verify, VbDecState *st_host);
 
 /* vb_encoder.cu */
 void vb_encoder_layers_dev(VbEngine *e, float *d_x, int new_len, int cache_len, int logical_start, int update_tail);

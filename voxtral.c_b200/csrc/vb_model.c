@@ -275,9 +275,48 @@ vox_ctx_t *vox_load(const char *model_dir) {
     return ctx;
 }
 
+/* A second context on the same weights: own decoder KV ring, encoder tail, scratch and counters; the bf16 matrices, the
+ * small f32 tensors (incl. the time conditioning: call vox_set_delay on the parent BEFORE forking), the host-side public
+ * tensors and the CUDA stream are the parent's.  One vox_stream_t per context, as in the reference (voxtral.c:1226-1228);
+ * forks exist so that several streams can share one weight pass (vox_cuda_streams_decode).  Free forks before the parent. */
+vox_ctx_t *vox_cuda_ctx_fork(vox_ctx_t *parent) {
+    if (!parent) return NULL;
+    VbEngine *pe = vb_engine(parent);
+    VbEngine *e = malloc(sizeof *e);
+    if (!e) return NULL;
+    memcpy(e, pe, sizeof *e);
+    e->parent = pe->parent ? pe->parent : pe;
+    e->owned = NULL; e->n_owned = e->cap_owned = 0;
+    e->d_kv_k = e->d_kv_v = NULL; e->kv_bytes = 0; e->d_state = NULL;
+    e->d_x = e->d_q = e->d_attn_out = e->d_gate = e->d_logits = NULL;
+    e->d_part_m = e->d_part_l = e->d_part_o = NULL; e->d_argmax = NULL;
+    e->d_tokens = NULL; e->tokens_cap = 0; e->h_tokens_pinned = NULL; e->d_embed_in = NULL;
+    e->d_tc_img = NULL; e->d_mega_bar = NULL; e->step_graph_ready = 0;
+    memset(&e->v2, 0, sizeof e->v2);
+    memset(e->ws, 0, sizeof e->ws); memset(e->ws_bytes, 0, sizeof e->ws_bytes);
+    e->d_enc_tail_k = e->d_enc_tail_v = NULL; e->enc_tail_len = 0;
+    e->launches = 0; e->last_decode_ms = e->last_encoder_ms = e->last_mel_ms = 0; e->last_decode_steps = e->last_encoder_positions = 0;
+    e->total_decode_ms = e->total_encoder_ms = 0; e->total_decode_steps = e->total_encoder_positions = 0;
+    vox_ctx_t *c = &e->pub;
+    c->kv_cache_len = c->kv_cache_max = c->kv_pos_offset = 0;
+    c->enc_kv_cache_len = c->enc_kv_cache_max = c->enc_kv_pos_offset = 0;
+    if (cudaSetDevice(e->device) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+        cudaEventCreate(&e->ev_user0) != cudaSuccess || cudaEventCreate(&e->ev_user1) != cudaSuccess) { free(e); return NULL; }
+    const size_t wb = e->weight_bytes;
+    vb_decoder_alloc(e);
+    e->weight_bytes = wb;
+    return c;
+}
+
 void vox_free(vox_ctx_t *ctx) {
     if (!ctx) return;
     VbEngine *e = vb_engine(ctx);
+    if (e->parent) {                                       /* a fork owns only its KV / scratch / events */
+        vb_decoder_free(e);
+        vb_device_shutdown(e);
+        free(e);
+        return;
+    }
 #define FREE0(p) do { free(p); (p) = NULL; } while (0)
     FREE0(ctx->encoder.conv0_weight); FREE0(ctx->encoder.conv0_bias);
     FREE0(ctx->encoder.conv1_weight); FREE0(ctx->encoder.conv1_bias);

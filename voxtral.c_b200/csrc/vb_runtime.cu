@@ -61,12 +61,12 @@ extern "C" void vb_device_shutdown(VbEngine *e) {
     cudaStreamSynchronize(e->stream);
     for (int i = 0; i < e->n_owned; i++) cudaFree(e->owned[i]);
     free(e->owned); e->owned = NULL; e->n_owned = 0;
-    free(e->mirrors); e->mirrors = NULL; e->n_mirrors = 0;
+    if (!e->parent) { free(e->mirrors); e->mirrors = NULL; e->n_mirrors = 0; }
     for (int i = 0; i < VB_WS_SLOTS; i++) { cudaFree(e->ws[i]); e->ws[i] = NULL; e->ws_bytes[i] = 0; }
     if (e->step_graph_ready) cudaGraphExecDestroy(e->step_graph);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->ev_user0); cudaEventDestroy(e->ev_user1);
-    cudaStreamDestroy(e->stream);
+    if (!e->parent) cudaStreamDestroy(e->stream);
     e->stream = NULL;
     if (g_default_engine == e) g_default_engine = NULL;
 }

@@ -66,6 +66,7 @@ struct vox_stream {
     int nontext_streak, text_since_restart, empty_restarts, waiting_prompt;
     int64_t last_decode_sample;
     int finished, continuous;
+    int defer_decode;         /* vox_cuda_stream_set_deferred: feed/flush/finish stop after the adapter; vox_cuda_streams_decode runs the decoder */
 
     const char **token_queue;
     int queue_head, queue_tail, queue_cap;
@@ -361,8 +362,31 @@ static int generate(vox_stream_t *s, int n, step_stats *st) {
     return produced;
 }
 
-static void run_decoder(vox_stream_t *s) {
+/* Prompt prefill + the first decode step (voxtral.c:990-1012).  Prompt embeddings for positions 0..prompt_len-2 are
+ * prefilled; the last prompt position is an ordinary decode step whose "previous token" is STREAMING_PAD. */
+static void start_decoder(vox_stream_t *s) {
     VbEngine *e = s->e;
+    vox_ctx_t *c = s->ctx;
+    const int prompt_len = 1 + 32 + c->delay_tokens;
+    s->waiting_prompt = 0;
+    double t0 = now_ms();
+    int pre = prompt_len - 1;
+    float *prompt = vb_ws(e, WS_PROMPT, (size_t)pre * VOX_DEC_DIM * 4);
+    vb_build_prompt_dev(e, prompt, s->d_adapter, pre, TOKEN_BOS, TOKEN_STREAMING_PAD);
+    c->kv_cache_len = 0; c->kv_pos_offset = 0;
+    if (c->kv_cache_max == 0) c->kv_cache_max = VOX_DEC_WINDOW + pre + 1024;      /* kv_cache_init, voxtral_decoder.c:423 */
+    vb_decoder_prefill_dev(e, prompt, pre, 0);
+    c->kv_cache_len = pre;
+    s->gen_pos = s->adapter_pos_offset + pre;
+    s->prev_token = TOKEN_STREAMING_PAD;
+    generate(s, 1, NULL);
+    s->decoder_started = 1;
+    double dt = now_ms() - t0;
+    s->decoder_ms += dt; s->prefill_ms += dt;
+    if (vox_monitor) { fprintf(stderr, "\xc2\xb7"); fflush(stderr); }
+}
+
+static void run_decoder(vox_stream_t *s) {
     vox_ctx_t *c = s->ctx;
     const int prompt_len = 1 + 32 + c->delay_tokens;
     int cur = s->total_adapter - s->adapter_pos_offset;
@@ -371,26 +395,7 @@ static void run_decoder(vox_stream_t *s) {
         if (vox_monitor && !s->waiting_prompt) { fprintf(stderr, "\xe2\x8c\x9b"); fflush(stderr); s->waiting_prompt = 1; }
         return;
     }
-    if (!s->decoder_started) {
-        s->waiting_prompt = 0;
-        double t0 = now_ms();
-        /* prompt embeddings for positions 0..prompt_len-2 are prefilled; the last prompt position is an
-         * ordinary decode step whose "previous token" is STREAMING_PAD (voxtral.c:990-1012) */
-        int pre = prompt_len - 1;
-        float *prompt = vb_ws(e, WS_PROMPT, (size_t)pre * VOX_DEC_DIM * 4);
-        vb_build_prompt_dev(e, prompt, s->d_adapter, pre, TOKEN_BOS, TOKEN_STREAMING_PAD);
-        c->kv_cache_len = 0; c->kv_pos_offset = 0;
-        if (c->kv_cache_max == 0) c->kv_cache_max = VOX_DEC_WINDOW + pre + 1024;      /* kv_cache_init, voxtral_decoder.c:423 */
-        vb_decoder_prefill_dev(e, prompt, pre, 0);
-        c->kv_cache_len = pre;
-        s->gen_pos = s->adapter_pos_offset + pre;
-        s->prev_token = TOKEN_STREAMING_PAD;
-        generate(s, 1, NULL);
-        s->decoder_started = 1;
-        double dt = now_ms() - t0;
-        s->decoder_ms += dt; s->prefill_ms += dt;
-        if (vox_monitor) { fprintf(stderr, "\xc2\xb7"); fflush(stderr); }
-    }
+    if (!s->decoder_started) start_decoder(s);
 
     if (s->decoder_started && !s->eos_seen && s->gen_pos < s->total_adapter) {
         double t0 = now_ms();
@@ -471,7 +476,7 @@ int vox_stream_feed(vox_stream_t *s, const float *samples, int n_samples) {
     vox_mel_feed(s->mel, samples, n_samples);
     s->real_samples_fed += n_samples;
     run_encoder(s);
-    run_decoder(s);
+    if (!s->defer_decode) run_decoder(s);
     return 0;
 }
 
@@ -481,7 +486,7 @@ int vox_cuda_stream_feed_device(vox_stream_t *s, const float *d_samples, int n_s
     vb_mel_feed_device(s->mel, d_samples, n_samples);
     s->real_samples_fed += n_samples;
     run_encoder(s);
-    run_decoder(s);
+    if (!s->defer_decode) run_decoder(s);
     return 0;
 }
 
@@ -494,7 +499,7 @@ int vox_stream_flush(vox_stream_t *s) {
     int saved = s->min_new_mel;
     s->min_new_mel = 1;
     run_encoder(s);
-    run_decoder(s);
+    if (!s->defer_decode) run_decoder(s);
     s->min_new_mel = saved;
     return 0;
 }
@@ -508,7 +513,7 @@ int vox_stream_finish(vox_stream_t *s) {
         fprintf(stderr, "Stream finished: %lld real samples (%.1f sec)\n", (long long)s->real_samples_fed,
                 (double)s->real_samples_fed / VOX_SAMPLE_RATE);
     run_encoder(s);
-    run_decoder(s);
+    if (!s->defer_decode) run_decoder(s);
     return 0;
 }
 
@@ -567,6 +572,82 @@ void vox_stream_free(vox_stream_t *s) {
     cudaFree(s->d_conv0_resid); cudaFree(s->d_enc_resid);
     free(s->token_queue); free(s->ids); free(s->tok_buf);
     free(s);
+}
+
+/* ---------------------------------------------------------------- several streams, one weight pass */
+/* A decode step reads 6.86 GB of weights whatever the number of activation columns, so up to 8 streams on one GPU share every
+ * weight byte (vb_decode_v2.cu).  Each stream lives on its own context (vox_cuda_ctx_fork: own KV ring / encoder tail / scratch,
+ * shared weights and CUDA stream) and is put in deferred mode, where feed/flush/finish run mel -> encoder -> adapter only;
+ * vox_cuda_streams_decode() then advances the decoders of all of them together until every stream has consumed its adapter rows.
+ * Per stream the result is what run_decoder() would have produced (same kernels, same per-column arithmetic); the live-stream
+ * restart policy (vox_stream_set_continuous) and alternatives (n_alt > 1) need per-step host decisions and stay single-stream. */
+void vox_cuda_stream_set_deferred(vox_stream_t *s, int on) { if (s) s->defer_decode = on ? 1 : 0; }
+
+int vox_cuda_streams_decode(vox_stream_t **ss, int n) {
+    if (!ss || n < 1 || n > 8) return -1;
+    VbEngine *lead = ss[0]->e;
+    for (int i = 0; i < n; i++) {
+        vox_stream_t *s = ss[i];
+        if (!s || s->continuous || s->n_alt > 1 || s->e->device != lead->device || s->e->stream != lead->stream) {
+            fprintf(stderr, "vox_cuda_streams_decode: stream %d cannot be batched (continuous mode, alternatives, or another device/ctx group)\n", i);
+            return -1;
+        }
+    }
+    VB_CUDA_OK(cudaSetDevice(lead->device));
+    int total = 0;
+    for (int i = 0; i < n; i++) {                         /* prompts: per-stream prefill (tcgen05 GEMMs) + first step */
+        vox_stream_t *s = ss[i];
+        const int prompt_len = 1 + 32 + s->ctx->delay_tokens;
+        if (!s->decoder_started && s->total_adapter - s->adapter_pos_offset >= prompt_len) { start_decoder(s); total++; }
+    }
+    if (!vb_decoder_v2_supported(lead)) {                  /* no batched kernel on this device: one stream after the other */
+        for (int i = 0; i < n; i++) { int before = ss[i]->n_generated; run_decoder(ss[i]); total += ss[i]->n_generated - before; }
+        return total;
+    }
+    double t0 = now_ms();
+    for (;;) {
+        VbV2Col cols[8]; int who[8]; int nb = 0, longest = 0;
+        for (int i = 0; i < n; i++) {
+            vox_stream_t *s = ss[i];
+            int pending = s->total_adapter - s->gen_pos;
+            if (!s->decoder_started || s->eos_seen || pending <= 0) continue;
+            VbV2Col *c = &cols[nb];
+            c->engine = s->e; c->d_adapter = s->d_adapter; c->adapter_row = s->gen_pos - s->adapter_pos_offset;
+            c->n_steps = pending; c->prev_token = s->prev_token; c->pos = s->ctx->kv_pos_offset + s->ctx->kv_cache_len;
+            if (pending > longest) longest = pending;
+            who[nb++] = i;
+        }
+        if (nb == 0) break;
+        VbDecState st[8];
+        cudaEvent_t e0 = lead->ev0, e1 = lead->ev1;
+        VB_CUDA_OK(cudaEventRecord(e0, lead->stream));
+        if (vb_decoder_v2_launch(lead, cols, nb, longest, 0, st) != 0) return -1;
+        VB_CUDA_OK(cudaEventRecord(e1, lead->stream));
+        cudaError_t serr = cudaStreamSynchronize(lead->stream);
+        if (serr != cudaSuccess) { fprintf(stderr, "vox_cuda_streams_decode: decode kernel failed: %s\n", cudaGetErrorString(serr)); return -1; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        int steps = 0;
+        for (int b = 0; b < nb; b++) {
+            vox_stream_t *s = ss[who[b]];
+            int got = st[b].n_out;
+            if (got > steps) steps = got;
+            if (got <= 0) continue;
+            if (got > s->tok_buf_cap) { s->tok_buf_cap = got + 256; s->tok_buf = realloc(s->tok_buf, sizeof(int) * (size_t)s->tok_buf_cap); }
+            vb_d2h_sync(s->e, s->tok_buf, s->e->d_tokens, (size_t)got * 4);
+            for (int i = 0; i < got; i++) {
+                kv_counters_step(s->ctx);
+                on_token(s, s->tok_buf[i], NULL);
+                s->gen_pos++; total++;
+                if (s->eos_seen) break;
+            }
+        }
+        lead->last_decode_ms = ms; lead->last_decode_steps = steps;
+        lead->total_decode_ms += ms; lead->total_decode_steps += steps;
+        if (steps == 0) break;
+    }
+    double dt = now_ms() - t0;
+    for (int i = 0; i < n; i++) { ss[i]->decoder_ms += dt / n; adapter_compact(ss[i]); }
+    return total;
 }
 
 /* ---------------------------------------------------------------- introspection (section 7 of the header) */
