@@ -423,6 +423,11 @@ double vox_cuda_timer_stop_ms(vox_ctx_t *ctx);
 int vox_cuda_debug_copy_kv(vox_ctx_t *ctx, int layer, float *h_k, float *h_v);
 int vox_cuda_debug_copy_logits(vox_ctx_t *ctx, float *h_logits);
 
+/* Test hook for the error paths: the n-th device allocation from now on, and every later one, fails with an out-of-memory
+ * error (n < 0: off).  With it vox_load returns NULL, vox_stream_init NULL, vox_stream_feed/flush/finish -1 -- the
+ * reference's error returns (voxtral.c:132-158,1199-1200,1237) instead of a process abort. */
+void vox_cuda_debug_fail_alloc_after(long long n);
+
 /* Copy the device stream state a test wants to inspect back to the host. */
 int vox_cuda_stream_token_ids(vox_stream_t *s, int *out, int max);   /* all ids generated so far */
 int vox_cuda_stream_counts(vox_stream_t *s, int *mel_frames, int *adapter_tokens,

@@ -40,7 +40,11 @@ def check_against(g, ids, text):
     for i, (a, b) in enumerate(zip(ids, ref_ids)):
         if a != b:
             assert not ok[i], f"token mismatch at step {i}: {a} vs {b} (reference margin {g['top_val'][i,0]-g['top_val'][i,1]:.3e})"
-            pytest.skip(f"near-tie flip at step {i}; later steps are not comparable")
+            # a flip where the reference's own top-2 margin is below 2e-3 is legitimate (the reference flips between its own
+            # builds there, runtest.sh:24-26), but it makes every later step incomparable: report it as an expected failure
+            # so it stays visible instead of hiding the rest of the run behind a skip
+            pytest.xfail(f"near-tie flip at step {i} of {len(ref_ids)} (reference margin {g['top_val'][i,0]-g['top_val'][i,1]:.3e}); "
+                         f"{i} steps matched, later steps are not comparable")
     assert text == g["text"].tobytes()
 
 

@@ -110,6 +110,7 @@ def lib():
         "vox_cuda_timer_start": (None, [vp]), "vox_cuda_timer_stop_ms": (C.c_double, [vp]),
         "vox_cuda_stream_token_ids": (i, [vp, c_int_p, i]),
         "vox_cuda_stream_counts": (i, [vp, c_int_p, c_int_p, c_int_p]),
+        "vox_cuda_debug_fail_alloc_after": (None, [C.c_longlong]),
         "vox_cuda_ctx_fork": (vp, [vp]), "vox_cuda_stream_set_deferred": (None, [vp, i]),
         "vox_cuda_streams_decode": (i, [C.POINTER(vp), i]),
     }

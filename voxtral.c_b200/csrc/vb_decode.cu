@@ -391,7 +391,7 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
             VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
             if (driver == 5) {
                 VbV2Col col = { e, d_adapter, adapter_row + done, chunk, prev_token, pos + done };
-                if (vb_decoder_v2_launch(e, &col, 1, chunk, 0, NULL) != 0) { fprintf(stderr, "voxtral_b200: v2 decode launch failed\n"); abort(); }
+                if (vb_decoder_v2_launch(e, &col, 1, chunk, 0, NULL) != 0) VB_FAIL("v2 decode launch failed");
             } else if (driver == 2) vb_decoder_mega_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             else if (driver == 4) vb_decoder_tc_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             else vb_decoder_persist_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
@@ -417,7 +417,7 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
         cudaError_t serr = cudaStreamSynchronize(e->stream);
         if (serr != cudaSuccess) {
             fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), driver == 1 ? "graph" : driver == 2 ? "tma-ring" : driver == 4 ? "tc-ring" : driver == 5 ? "v2" : "persist");
-            abort();
+            vb_cuda_fail(serr, __FILE__, __LINE__);
         }
         VB_CUDA_OK(cudaMemcpy(e->h_tokens_pinned, e->d_tokens, (size_t)st.n_out * 4, cudaMemcpyDeviceToHost));
         float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); total_ms += ms;

@@ -294,7 +294,8 @@ __device__ __forceinline__ void v2_dot8(const uint4 w, const V2X<NB> &x, float (
 template <int NB, typename Epi>
 __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uint32_t &it, int seg_bytes, int NT,
                                            const V2X<NB> &x, int &redbuf, int *err, Epi epi) {
-    constexpr int R = V2_RC * NB;
+    constexpr int RG = NB >= 4 ? 2 : V2_RC;           /* rows per reduction group (register budget: 128 per thread) */
+    constexpr int R = RG * NB;                         /* values reduced together */
     constexpr int LG = V2Log2<R>::v;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const bool active = t < NT;
@@ -304,38 +305,44 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
         long long t0 = 0;
         while (!mbar_try_wait(&sm->full[s], par)) spin_guard(t0, err, 3);
         const int nrows = sm->meta_nrows[s], row0 = sm->meta_row0[s];
-        float acc[R];
+        const uint8_t *base = slots + (size_t)s * V2_SLOT_BYTES + (size_t)t * 16;
+        if (nrows > 0) {
 #pragma unroll
-        for (int i = 0; i < R; i++) acc[i] = 0.f;
-        if (nrows > 0 && active) {
-            const uint8_t *base = slots + (size_t)s * V2_SLOT_BYTES + (size_t)t * 16;
-            uint4 w[V2_RC];
+            for (int h = 0; h < V2_RC / RG; h++) {
+                float acc[R];
 #pragma unroll
-            for (int r = 0; r < V2_RC; r++) w[r] = (r < nrows) ? *reinterpret_cast<const uint4 *>(base + (size_t)r * seg_bytes) : make_uint4(0u, 0u, 0u, 0u);
+                for (int i = 0; i < R; i++) acc[i] = 0.f;
+                if (active) {
+                    uint4 w[RG];
 #pragma unroll
-            for (int r = 0; r < V2_RC; r++) {
-                float a[NB];
+                    for (int r = 0; r < RG; r++)
+                        w[r] = (h * RG + r < nrows) ? *reinterpret_cast<const uint4 *>(base + (size_t)(h * RG + r) * seg_bytes) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int b = 0; b < NB; b++) a[b] = 0.f;
-                v2_dot8<NB>(w[r], x, a);
+                    for (int r = 0; r < RG; r++) {
+                        float a[NB];
 #pragma unroll
-                for (int b = 0; b < NB; b++) acc[r * NB + b] = a[b];
+                        for (int b = 0; b < NB; b++) a[b] = 0.f;
+                        v2_dot8<NB>(w[r], x, a);
+#pragma unroll
+                        for (int b = 0; b < NB; b++) acc[r * NB + b] = a[b];
+                    }
+                }
+                const float tot = v2_transpose_reduce<R>(acc, lane);
+                if ((lane & ((32 >> LG) - 1)) == 0) sm->red[redbuf][warp][h * R + (lane >> (5 - LG))] = tot;
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->empty[s]);
         it++;
         if (nrows == 0) break;
-        const float tot = v2_transpose_reduce<R>(acc, lane);
-        if ((lane & ((32 >> LG) - 1)) == 0) sm->red[redbuf][warp][lane >> (5 - LG)] = tot;
         v2_bar();
         if (warp == V2_CW - 1) {
             float sum = 0.f;
-            if (lane < R) {
+            if (lane < V2_RC * NB) {
 #pragma unroll
                 for (int wv = 0; wv < V2_CW; wv++) sum += sm->red[redbuf][wv][lane];
             }
-            epi(row0 + lane / NB, lane % NB, sum, lane, lane < R && lane / NB < nrows);
+            epi(row0 + lane / NB, lane % NB, sum, lane, lane < V2_RC * NB && lane / NB < nrows);
         }
         redbuf ^= 1;
     }
@@ -533,7 +540,7 @@ extern __shared__ __align__(1024) uint8_t v2_smem_raw[];
     a.prof[(size_t)blockIdx.x * V2_PROF_SLOTS + prof_n++] = clock64(); } while (0)
 
 template <int NB>
-__global__ void __maxnreg__(152) k_dec_v2(const __grid_constant__ V2Args a) {
+__global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant__ V2Args a) {
     uint8_t *slots = v2_smem_raw;
     float *att_scr = reinterpret_cast<float *>(v2_smem_raw + (size_t)V2_SLOTS * V2_SLOT_BYTES);
     V2Smem *sm = reinterpret_cast<V2Smem *>(v2_smem_raw + (size_t)V2_SLOTS * V2_SLOT_BYTES + (size_t)V2_ATT_FLOATS * 4);
@@ -724,9 +731,21 @@ extern "C" int vb_decoder_v2_supported(VbEngine *e) {
     int coop = 0, blocks = 0, smem_optin = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
-    if (!coop || e->sm_count > 8 * V2_NSPLIT_MAX || (size_t)smem_optin < v2_smem_bytes()) return 0;
-    if (v2_prepare<1>() != cudaSuccess || v2_prepare<2>() != cudaSuccess || v2_prepare<4>() != cudaSuccess || v2_prepare<8>() != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_dec_v2<8>, V2_THREADS, v2_smem_bytes()) != cudaSuccess || blocks < 1) return 0;
+    const char *why = NULL; cudaError_t ce = cudaSuccess;
+    if (!coop) why = "no cooperative launch";
+    else if (e->sm_count > 8 * V2_NSPLIT_MAX) why = "more SMs than the attention split supports";
+    else if ((size_t)smem_optin < v2_smem_bytes()) why = "not enough shared memory per block";
+    else if ((ce = v2_prepare<1>()) != cudaSuccess || (ce = v2_prepare<2>()) != cudaSuccess || (ce = v2_prepare<4>()) != cudaSuccess ||
+             (ce = v2_prepare<8>()) != cudaSuccess) why = "cudaFuncSetAttribute failed";
+    else if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_dec_v2<8>, V2_THREADS, v2_smem_bytes())) != cudaSuccess || blocks < 1)
+        why = "kernel does not fit one CTA per SM";
+    if (why) {
+        if (vox_verbose >= 1 || getenv("VOX_CUDA_DECODE"))
+            fprintf(stderr, "voxtral_b200: v2 decode kernel unavailable: %s (%s; smem need %zu of %d, blocks/SM %d)\n", why,
+                    cudaGetErrorString(ce), v2_smem_bytes(), smem_optin, blocks);
+        cudaGetLastError();
+        return 0;
+    }
     e->v2_ok = 1;
     return 1;
 }

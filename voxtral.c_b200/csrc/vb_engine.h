@@ -36,9 +36,30 @@
 #define VB_WS_SLOTS  24   /* 0-11: model blocks (see vb_encoder.cu), 12-23: stream pipeline */
 #define VB_WS_ALT    20   /* 8 floats: result of the alternatives kernel (vb_decode.cu) */
 
-#define VB_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) {                 \
-    fprintf(stderr, "voxtral_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__),        \
-            __FILE__, __LINE__, cudaGetErrorString(e__)); abort(); } } while (0)
+/* Error boundary.  Inside the library a failed CUDA call (cudaMalloc out of memory, a launch error...) reports through
+ * vb_cuda_fail().  Public entry points that have an error return in the reference -- vox_load -> NULL (voxtral.c:132-158),
+ * vox_stream_init -> NULL, vox_stream_feed/flush/finish -> -1, vox_decoder_forward -> 2 = EOS on out-of-memory
+ * (voxtral_decoder.c:621,649), the malloc'ing vox_encoder_forward* / vox_adapter_forward / vox_transcribe* -> NULL -- open a
+ * guard (VB_API_GUARD): a failure below them unwinds to the guard with longjmp and becomes that return value.  Entry points
+ * without an error return (the void kernel-surface wrappers) still abort() with a message, as does any failure outside a guard.
+ * Host memory held by the interrupted call is leaked; device state of the ctx/stream is undefined afterwards and the stream
+ * is marked failed. */
+#include <setjmp.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+extern __thread jmp_buf *vb_err_jmp;
+void vb_cuda_fail(cudaError_t err, const char *file, int line);
+#ifdef __cplusplus
+}
+#endif
+#define VB_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) vb_cuda_fail(e__, __FILE__, __LINE__); } while (0)
+#define VB_FAIL(msg) do { fprintf(stderr, "voxtral_b200: %s\n", msg); vb_cuda_fail(cudaErrorUnknown, __FILE__, __LINE__); } while (0)
+/* usage:  VB_API_GUARD({ cleanup; return -1; });  ...body...  VB_API_END;  (the block runs after a failure below) */
+#define VB_API_GUARD(on_fail) jmp_buf vb_jb__; jmp_buf *vb_prev__ = vb_err_jmp;                              \
+    if (setjmp(vb_jb__)) { vb_err_jmp = vb_prev__; cudaGetLastError(); on_fail }                               \
+    vb_err_jmp = &vb_jb__
+#define VB_API_END vb_err_jmp = vb_prev__
 
 #ifdef __cplusplus
 extern "C" {

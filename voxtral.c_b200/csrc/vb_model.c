@@ -246,9 +246,11 @@ vox_ctx_t *vox_load(const char *model_dir) {
     ctx->use_bf16 = 1;
     ctx->kv_cache_fp16 = 0;
 
+    VB_API_GUARD({ fprintf(stderr, "vox_load: loading failed (device allocation or copy error)\n"); vox_free(ctx); return NULL; });
     if (vb_device_init(e) != 0) {
         fprintf(stderr, "vox_load: no usable CUDA device; refusing to load (no CPU fallback)\n");
         free(e);
+        VB_API_END;
         return NULL;
     }
     char path[1024];
@@ -259,19 +261,21 @@ vox_ctx_t *vox_load(const char *model_dir) {
         fprintf(stderr, "vox_load: cannot open %s\n", path);
         vb_device_shutdown(e);
         free(e);
+        VB_API_END;
         return NULL;
     }
     ctx->safetensors = sf;
     if (vox_verbose >= 1) fprintf(stderr, "Loading weights...\n");
-    if (load_encoder(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load encoder\n"); vox_free(ctx); return NULL; }
-    if (load_adapter(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load adapter\n"); vox_free(ctx); return NULL; }
-    if (load_decoder(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load decoder\n"); vox_free(ctx); return NULL; }
+    if (load_encoder(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load encoder\n"); VB_API_END; vox_free(ctx); return NULL; }
+    if (load_adapter(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load adapter\n"); VB_API_END; vox_free(ctx); return NULL; }
+    if (load_decoder(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load decoder\n"); VB_API_END; vox_free(ctx); return NULL; }
     update_time_conditioning(e);
     vb_decoder_alloc(e);
     vb_set_default_engine(e);
     if (vox_verbose >= 1)
         fprintf(stderr, "Model loaded. (%.2f GB of weights resident in HBM on device %d)\n",
                 (double)e->weight_bytes / 1e9, e->device);
+    VB_API_END;
     return ctx;
 }
 

@@ -13,6 +13,19 @@ static VbEngine *g_default_engine = NULL;
 static VbEngine  g_bare_engine;          /* used by kernel wrappers when no model is loaded */
 static int       g_bare_ready = 0;
 
+extern "C" { __thread jmp_buf *vb_err_jmp = NULL; }
+
+extern "C" void vb_cuda_fail(cudaError_t err, const char *file, int line) {
+    fprintf(stderr, "voxtral_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err), file, line, cudaGetErrorString(err));
+    if (vb_err_jmp) longjmp(*vb_err_jmp, 1);
+    abort();
+}
+
+/* Test hook: VOX_CUDA_FAIL_ALLOC_AFTER=n makes the n-th device allocation from now on (and every later one) fail with
+ * cudaErrorMemoryAllocation, so the out-of-memory paths of the API can be exercised (tests/test_gpu_error_paths.py). */
+static long long g_alloc_budget = -1;
+extern "C" void vox_cuda_debug_fail_alloc_after(long long n) { g_alloc_budget = n; }
+
 extern "C" void vb_require_gpu(const char *what) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -73,6 +86,10 @@ extern "C" void vb_device_shutdown(VbEngine *e) {
 
 extern "C" void *vb_dev_alloc(size_t bytes) {
     void *p = NULL;
+    if (g_alloc_budget >= 0) {
+        if (g_alloc_budget == 0) vb_cuda_fail(cudaErrorMemoryAllocation, __FILE__, __LINE__);
+        g_alloc_budget--;
+    }
     VB_CUDA_OK(cudaMalloc(&p, bytes ? bytes : 16));
     return p;
 }
@@ -114,6 +131,7 @@ extern "C" float *vb_ws(VbEngine *e, int slot, size_t bytes) {
     if (bytes > e->ws_bytes[slot]) {
         VB_CUDA_OK(cudaStreamSynchronize(e->stream));
         cudaFree(e->ws[slot]);
+        e->ws[slot] = NULL; e->ws_bytes[slot] = 0;          /* a failed allocation below must not leave a dangling slot */
         size_t want = bytes + bytes / 8 + 256;
         e->ws[slot] = (float *)vb_dev_alloc(want);
         e->ws_bytes[slot] = want;

@@ -66,6 +66,7 @@ struct vox_stream {
     int nontext_streak, text_since_restart, empty_restarts, waiting_prompt;
     int64_t last_decode_sample;
     int finished, continuous;
+    int failed;               /* a CUDA/allocation failure unwound out of this stream: every later call returns -1 */
     int defer_decode;         /* vox_cuda_stream_set_deferred: feed/flush/finish stop after the adapter; vox_cuda_streams_decode runs the decoder */
 
     const char **token_queue;
@@ -79,6 +80,13 @@ struct vox_stream {
     int *ids; int n_ids, cap_ids;       /* every generated id, for introspection */
     int *tok_buf; int tok_buf_cap;
 };
+
+/* realloc that reports through the error boundary instead of dereferencing NULL later */
+static void *xrealloc(void *p, size_t bytes) {
+    void *q = realloc(p, bytes);
+    if (!q) { fprintf(stderr, "voxtral_b200: out of host memory (%zu bytes)\n", bytes); vb_cuda_fail(cudaErrorMemoryAllocation, __FILE__, __LINE__); }
+    return q;
+}
 
 static double now_ms(void) {
     struct timeval tv; gettimeofday(&tv, NULL);
@@ -133,7 +141,7 @@ static void fill_alts(vox_stream_t *s, int best, const char *alts[VOX_MAX_ALT]) 
 static void remember_id(vox_stream_t *s, int id) {
     if (s->n_ids == s->cap_ids) {
         s->cap_ids = s->cap_ids ? s->cap_ids * 2 : 1024;
-        s->ids = realloc(s->ids, sizeof(int) * (size_t)s->cap_ids);
+        s->ids = xrealloc(s->ids, sizeof(int) * (size_t)s->cap_ids);
     }
     s->ids[s->n_ids++] = id;
 }
@@ -343,7 +351,7 @@ static void on_token(vox_stream_t *s, int tok, step_stats *st) {
 static int generate(vox_stream_t *s, int n, step_stats *st) {
     VbEngine *e = s->e;
     vox_ctx_t *c = s->ctx;
-    if (n > s->tok_buf_cap) { s->tok_buf_cap = n + 256; s->tok_buf = realloc(s->tok_buf, sizeof(int) * (size_t)s->tok_buf_cap); }
+    if (n > s->tok_buf_cap) { s->tok_buf_cap = n + 256; s->tok_buf = xrealloc(s->tok_buf, sizeof(int) * (size_t)s->tok_buf_cap); }
     int produced = 0;
     while (produced < n && !s->eos_seen) {
         int want = s->n_alt > 1 ? 1 : n - produced;      /* alternatives are taken from each step's logits (still in HBM) */
@@ -450,12 +458,13 @@ vox_stream_t *vox_stream_init(vox_ctx_t *ctx) {
     if (!ctx) return NULL;
     vox_stream_t *s = calloc(1, sizeof *s);
     if (!s) return NULL;
+    VB_API_GUARD({ fprintf(stderr, "vox_stream_init: device allocation failed\n"); return NULL; });
     s->ctx = ctx; s->e = vb_engine(ctx);
     VB_CUDA_OK(cudaSetDevice(s->e->device));
     char path[1024];
     snprintf(path, sizeof path, "%s/tekken.json", ctx->model_dir);
     s->tokenizer = vox_tokenizer_load(path);
-    if (!s->tokenizer) { free(s); return NULL; }
+    if (!s->tokenizer) { free(s); VB_API_END; return NULL; }
     s->mel = vb_mel_ctx_init_on(s->e, 32 * SAMPLES_PER_TOKEN);
     s->queue_cap = 256;
     s->token_queue = calloc((size_t)s->queue_cap * VOX_MAX_ALT, sizeof *s->token_queue);
@@ -467,31 +476,37 @@ vox_stream_t *vox_stream_init(vox_ctx_t *ctx) {
     s->prev_token = TOKEN_BOS;
     ctx->enc_kv_cache_len = 0; ctx->enc_kv_pos_offset = 0;
     s->min_new_mel = (int)(DEFAULT_INTERVAL_S * 100.0f);
+    VB_API_END;
     return s;
 }
 
 int vox_stream_feed(vox_stream_t *s, const float *samples, int n_samples) {
-    if (!s || s->finished || n_samples <= 0) return -1;
+    if (!s || s->finished || s->failed || n_samples <= 0) return -1;
+    VB_API_GUARD({ s->failed = 1; return -1; });
     VB_CUDA_OK(cudaSetDevice(s->e->device));
     vox_mel_feed(s->mel, samples, n_samples);
     s->real_samples_fed += n_samples;
     run_encoder(s);
     if (!s->defer_decode) run_decoder(s);
+    VB_API_END;
     return 0;
 }
 
 int vox_cuda_stream_feed_device(vox_stream_t *s, const float *d_samples, int n_samples) {
-    if (!s || s->finished || n_samples <= 0) return -1;
+    if (!s || s->finished || s->failed || n_samples <= 0) return -1;
+    VB_API_GUARD({ s->failed = 1; return -1; });
     VB_CUDA_OK(cudaSetDevice(s->e->device));
     vb_mel_feed_device(s->mel, d_samples, n_samples);
     s->real_samples_fed += n_samples;
     run_encoder(s);
     if (!s->defer_decode) run_decoder(s);
+    VB_API_END;
     return 0;
 }
 
 int vox_stream_flush(vox_stream_t *s) {
-    if (!s || s->finished) return -1;
+    if (!s || s->finished || s->failed) return -1;
+    VB_API_GUARD({ s->failed = 1; return -1; });
     VB_CUDA_OK(cudaSetDevice(s->e->device));
     int align = (int)((SAMPLES_PER_TOKEN - (s->real_samples_fed % SAMPLES_PER_TOKEN)) % SAMPLES_PER_TOKEN);
     int right_pad = align + (s->ctx->delay_tokens + 1 + OFFLINE_BUFFER_TOKENS) * SAMPLES_PER_TOKEN;
@@ -501,12 +516,14 @@ int vox_stream_flush(vox_stream_t *s) {
     run_encoder(s);
     if (!s->defer_decode) run_decoder(s);
     s->min_new_mel = saved;
+    VB_API_END;
     return 0;
 }
 
 int vox_stream_finish(vox_stream_t *s) {
-    if (!s || s->finished) return -1;
-    vox_stream_flush(s);
+    if (!s || s->finished || s->failed) return -1;
+    if (vox_stream_flush(s) != 0) return -1;
+    VB_API_GUARD({ s->failed = 1; return -1; });
     s->finished = 1;
     vox_mel_finish(s->mel, 0);
     if (vox_verbose >= 2)
@@ -514,6 +531,7 @@ int vox_stream_finish(vox_stream_t *s) {
                 (double)s->real_samples_fed / VOX_SAMPLE_RATE);
     run_encoder(s);
     if (!s->defer_decode) run_decoder(s);
+    VB_API_END;
     return 0;
 }
 
@@ -593,6 +611,7 @@ int vox_cuda_streams_decode(vox_stream_t **ss, int n) {
             return -1;
         }
     }
+    VB_API_GUARD({ for (int i = 0; i < n; i++) ss[i]->failed = 1; return -1; });
     VB_CUDA_OK(cudaSetDevice(lead->device));
     int total = 0;
     for (int i = 0; i < n; i++) {                         /* prompts: per-stream prefill (tcgen05 GEMMs) + first step */
@@ -602,6 +621,7 @@ int vox_cuda_streams_decode(vox_stream_t **ss, int n) {
     }
     if (!vb_decoder_v2_supported(lead)) {                  /* no batched kernel on this device: one stream after the other */
         for (int i = 0; i < n; i++) { int before = ss[i]->n_generated; run_decoder(ss[i]); total += ss[i]->n_generated - before; }
+        VB_API_END;
         return total;
     }
     double t0 = now_ms();
@@ -621,10 +641,10 @@ int vox_cuda_streams_decode(vox_stream_t **ss, int n) {
         VbDecState st[8];
         cudaEvent_t e0 = lead->ev0, e1 = lead->ev1;
         VB_CUDA_OK(cudaEventRecord(e0, lead->stream));
-        if (vb_decoder_v2_launch(lead, cols, nb, longest, 0, st) != 0) return -1;
+        if (vb_decoder_v2_launch(lead, cols, nb, longest, 0, st) != 0) VB_FAIL("batched decode launch failed");
         VB_CUDA_OK(cudaEventRecord(e1, lead->stream));
         cudaError_t serr = cudaStreamSynchronize(lead->stream);
-        if (serr != cudaSuccess) { fprintf(stderr, "vox_cuda_streams_decode: decode kernel failed: %s\n", cudaGetErrorString(serr)); return -1; }
+        VB_CUDA_OK(serr);
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
         int steps = 0;
         for (int b = 0; b < nb; b++) {
@@ -632,7 +652,7 @@ int vox_cuda_streams_decode(vox_stream_t **ss, int n) {
             int got = st[b].n_out;
             if (got > steps) steps = got;
             if (got <= 0) continue;
-            if (got > s->tok_buf_cap) { s->tok_buf_cap = got + 256; s->tok_buf = realloc(s->tok_buf, sizeof(int) * (size_t)s->tok_buf_cap); }
+            if (got > s->tok_buf_cap) { s->tok_buf_cap = got + 256; s->tok_buf = xrealloc(s->tok_buf, sizeof(int) * (size_t)s->tok_buf_cap); }
             vb_d2h_sync(s->e, s->tok_buf, s->e->d_tokens, (size_t)got * 4);
             for (int i = 0; i < got; i++) {
                 kv_counters_step(s->ctx);
@@ -647,6 +667,7 @@ int vox_cuda_streams_decode(vox_stream_t **ss, int n) {
     }
     double dt = now_ms() - t0;
     for (int i = 0; i < n; i++) { ss[i]->decoder_ms += dt / n; adapter_compact(ss[i]); }
+    VB_API_END;
     return total;
 }
 
@@ -681,7 +702,7 @@ static void sb_drain(strbuf *sb, vox_stream_t *s) {
     while ((n = vox_stream_get(s, toks, 64)) > 0)
         for (int i = 0; i < n; i++) {
             size_t l = strlen(toks[i]);
-            if (sb->len + l + 1 > sb->cap) { while (sb->len + l + 1 > sb->cap) sb->cap *= 2; sb->p = realloc(sb->p, sb->cap); }
+            if (sb->len + l + 1 > sb->cap) { while (sb->len + l + 1 > sb->cap) sb->cap *= 2; sb->p = xrealloc(sb->p, sb->cap); }
             memcpy(sb->p + sb->len, toks[i], l + 1);
             sb->len += l;
         }
@@ -690,8 +711,10 @@ static void sb_drain(strbuf *sb, vox_stream_t *s) {
 char *vox_transcribe_audio(vox_ctx_t *ctx, const float *samples, int n_samples) {
     vox_stream_t *s = vox_stream_init(ctx);
     if (!s) return NULL;
-    vox_stream_feed(s, samples, n_samples);
-    vox_stream_finish(s);
+    if (vox_stream_feed(s, samples, n_samples) != 0 || vox_stream_finish(s) != 0) {
+        if (s->failed) { vox_stream_free(s); return NULL; }      /* device failure; n_samples <= 0 still yields "" like the reference */
+        if (!s->finished) vox_stream_finish(s);
+    }
     strbuf sb = { malloc(1024), 0, 1024 };
     sb.p[0] = 0;
     sb_drain(&sb, s);
@@ -721,7 +744,7 @@ char *vox_transcribe_stdin(vox_ctx_t *ctx) {
         uint8_t *buf = malloc(cap);
         memcpy(buf, head, 4);
         for (;;) {
-            if (size == cap) { cap *= 2; buf = realloc(buf, cap); }
+            if (size == cap) { cap *= 2; buf = xrealloc(buf, cap); }
             size_t got = fread(buf + size, 1, cap - size, stdin);
             if (!got) break;
             size += got;
@@ -784,12 +807,15 @@ void vox_decoder_prefill(vox_ctx_t *ctx, const float *input_embeds, int seq_len)
 
 int vox_decoder_forward(vox_ctx_t *ctx, const float *input_embeds, float *logits) {  /* voxtral_decoder.c:586 */
     VbEngine *e = vb_engine(ctx);
+    VB_API_GUARD({ return TOKEN_EOS; });               /* out of memory -> EOS, voxtral_decoder.c:621,649 */
     VB_CUDA_OK(cudaSetDevice(e->device));
     if (ctx->kv_cache_max == 0) ctx->kv_cache_max = VOX_DEC_WINDOW + 1024;
     kv_counters_step(ctx);
     int pos = ctx->kv_pos_offset + ctx->kv_cache_len - 1;
     vb_h2d(e, e->d_embed_in, input_embeds, (size_t)VOX_DEC_DIM * 4);
-    return vb_decoder_step_from_embed(e, e->d_embed_in, pos, logits);
+    int tok = vb_decoder_step_from_embed(e, e->d_embed_in, pos, logits);
+    VB_API_END;
+    return tok;
 }
 
 int vox_cuda_decoder_prefill(vox_ctx_t *ctx, const float *d_embeds, int n) {
