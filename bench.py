@@ -15,6 +15,15 @@ replicated weights (configs[3]), no data-path collective; weak scaling.
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, built from /root/reference by oracle/Makefile)
          timed on this box's host cores on a bounded sample of the same workload
 
+  parity_prefix  the ids of the benchmarked recording are compared, inside this run, with the reference's own trace of its
+         first 60 s (tests/golden/synth_s60_oneshot.npz, oracle/ref_trace on the unmodified reference; the synthetic PCM and
+         both models are causal, so that trace is the reference prefix of the 10-minute run)
+  multistream  8 copies of the same recording on forked contexts, decoded by ONE persistent kernel per launch
+         (vox_cuda_streams_decode: one weight pass for all streams); aggregate audio-s / device-s, ids equal to the
+         single-stream run
+  sharded_encoder  (N > 1) one 1-hour recording, encoder sharded by sequence over the N GPUs in host C with NCCL
+         (vox_cuda_encode_sharded: per-layer K/V halo ncclSend/ncclRecv + adapter ncclAllGather), vs the same call unsharded
+
 `--impl reference` times only that CPU reference arm.  The model is the seeded synthetic checkpoint
 (tools/make_synth_model.c): there is no network for the real weights; throughput does not depend on them.
 """
@@ -98,7 +107,7 @@ def peaks():
 # ----------------------------------------------------------------------------------------------
 # CPU reference arm: oracle/_ref (the reference's own sources compiled by oracle/Makefile)
 # ----------------------------------------------------------------------------------------------
-def reference_sample(model_dir, seconds, enc_positions=64, dec_steps=6):
+def reference_sample(model_dir, seconds, enc_positions=1024, dec_steps=16):
     """Bounded sample of the workload on the host cores: stream mel of 30 s, one incremental encoder call,
     the 38-token prefill and `dec_steps` single-token forwards; extrapolated to the full recording."""
     refp = os.path.join(ROOT, "oracle", "_ref", "libvoxref.so")
@@ -135,20 +144,41 @@ def reference_sample(model_dir, seconds, enc_positions=64, dec_steps=6):
     for s in range(dec_steps):
         R.vox_decoder_forward(ctx, P(emb[38 + s].copy()), P(lg))
     t_step = (time.perf_counter() - t) / dec_steps
+    R.vox_free.argtypes = [vp]; R.vox_free(ctx)
     frames, pos, toks, steps = expected_counts(int(seconds * 16000))
     total = seconds * t_mel + pos * (t_enc + t_ad) / enc_positions + t_pre + steps * t_step
-    return {"rtf": seconds / total, "tok_s": 1.0 / t_step, "cores": cores,
+    return {"rtf": seconds / total, "tok_s": 1.0 / t_step, "cores": cores, "extrapolated": True,
+            "measured": {"decoder_ms_per_forward": t_step * 1e3, "prefill_38_s": t_pre, "encoder_s_per_position": (t_enc + t_ad) / enc_positions,
+                         "mel_s_per_audio_s": t_mel},
             "wall_sample_s": 30 * t_mel + t_enc + t_ad + t_pre + dec_steps * t_step,
             "sample": (f"reference build timed on host: {dec_steps} decoder forwards ({t_step*1e3:.0f} ms/step, single-threaded "
                        f"by construction), 38-token prefill ({t_pre:.2f} s), one {enc_positions}-position incremental encoder "
                        f"call + adapter ({(t_enc+t_ad):.2f} s, OpenBLAS {cores} threads), 30 s of streaming mel; "
-                       f"extrapolated to the {seconds:g} s recording ({steps} steps, {pos} positions)")}
+                       f"EXTRAPOLATED linearly to the {seconds:g} s recording ({steps} steps, {pos} positions)")}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of k_dec_persist from one `ncu --set full` capture, divided by the 385 steps of
-# that launch (KV positions 38..423, so almost no KV traffic).  Not measured by this script: ncu cannot run inside a timed bench.
-NCU_DRAM_BYTES_PER_STEP = 6.56e9 + 0.95e6
-NCU_TRAFFIC_SOURCE = "profiles/r01_decode.md (ncu --set full, 30 s clip, per step)"
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per step, read from the committed raw export of one
+    `ncu --set full` capture (profiles/r02_decode_ncu_raw.csv: one launch = `steps` decode steps of a 30 s clip).  Not measured
+    by this script: ncu cannot run inside a timed bench."""
+    path = os.path.join(ROOT, "profiles", "r02_decode_ncu_raw.csv")
+    meta = os.path.join(ROOT, "profiles", "r02_decode_ncu_raw.json")
+    try:
+        steps = json.load(open(meta))["steps_in_launch"]
+        import csv
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        unit = rows[1]
+        data = rows[2]
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            k = hdr.index(name)
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit[k]]
+            tot += float(data[k].replace(",", "")) * mult
+        return tot / steps, "profiles/r02_decode_ncu_raw.csv (ncu --set full, one launch, per step)"
+    except Exception:
+        return None, "no committed ncu export"
+
 
 
 def main():
@@ -158,6 +188,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=600.0)
+    ap.add_argument("--streams", type=int, default=8, help="streams per GPU in the multistream leg (N=1 only; 1 = skip)")
+    ap.add_argument("--sharded-seconds", type=float, default=3600.0, help="recording length of the sharded-encoder leg (N>1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -171,7 +203,7 @@ def main():
         model, _ = ensure_inputs(min(args.seconds, 2.0))
         vals, last = [], None
         for i in range(args.warmup + args.steps):
-            last = reference_sample(model, args.seconds, enc_positions=32, dec_steps=3)
+            last = reference_sample(model, args.seconds)
             if last is None:
                 print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvoxref.so not built"}))
                 return
@@ -184,6 +216,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 activations x bf16 weights",
             "data": "synthetic", "config": {"workload": workload},
             "decoder_tok_s": last["tok_s"],
+            "reference_extrapolated": True, "reference_measured": last["measured"],
             "cpu_baseline": {"value": v, "unit": "x real-time", "cores": last["cores"], "kind": "reference", "sample": last["sample"]},
             "e2e": {"value": v, "unit": "x real-time", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -208,9 +241,11 @@ def main():
     import vbload
     vb = vbload.load()
     multi = vbload.load_submodule("multi")
+    t_load = time.perf_counter()
     eng = vb.Engine(model)
-    info0 = eng.info()
+    load_s = time.perf_counter() - t_load
     d_pcm = eng.to_device(pcm)
+    profiling = os.environ.get("VOX_BENCH_PROFILE") == "1"      # ncu runs: fewer warm-ups, no extra legs (never a bench value)
 
     def one_pass(device_input):
         s = eng.stream()
@@ -224,12 +259,12 @@ def main():
         s.close()
         return ids, c
 
-    def timed(k, device_input):
+    def timed(k, fn):
         barrier()
         eng.timer_start()
         t0 = time.perf_counter()
         for _ in range(k):
-            ids, c = one_pass(device_input)
+            out = fn()
         dev_ms = eng.timer_stop_ms()
         wall = time.perf_counter() - t0
         if dist is not None:
@@ -237,18 +272,21 @@ def main():
             dev_ms, wall_ms = multi.reduce_max([dev_ms, wall * 1e3], dist, torch.device("cuda", local))
             wall = wall_ms / 1e3
         barrier()
-        return dev_ms, wall, ids, c
+        return dev_ms, wall, out
 
-    profiling = os.environ.get("VOX_BENCH_PROFILE") == "1"      # ncu runs: fewer warm-ups, no CPU leg (never a bench value)
     n_warm = args.warmup if profiling else max(args.warmup, 3)
     for _ in range(n_warm):
         ids, counts = one_pass(True)
     sampler = ClockSampler(local); sampler.start()
     i_before = eng.info()
-    dev_ms, _, ids, counts = timed(args.steps, True)
+    dev_ms, _, (ids, counts) = timed(args.steps, lambda: one_pass(True))
     i_after = eng.info()
     sampler.stop.set(); sampler.join(timeout=3)
-    e2e_ms, e2e_wall, ids2, _ = timed(args.steps, False)
+    e2e_ms, e2e_wall, (ids2, _) = timed(args.steps, lambda: one_pass(False))
+
+    # the work that was timed is the work the reference would do on this recording (an early EOS would shrink it silently)
+    assert (counts["mel_frames"], counts["adapter_tokens"], len(ids)) == (frames, toks, steps_expected), \
+        (counts, len(ids), (frames, toks, steps_expected))
 
     audio_s = args.seconds * args.steps * world
     value = audio_s / (dev_ms / 1e3)
@@ -258,13 +296,73 @@ def main():
     n_dec = len(ids)
     # KV rows read by step i (position 38+i): min(pos+1, 8192) slots
     kv_slots = np.minimum(np.arange(38, 38 + n_dec) + 1, 8192).astype(np.float64)
-    bytes_per_step = WEIGHT_BYTES_PER_STEP + KV_BYTES_PER_SLOT * float(kv_slots.mean()) if n_dec else WEIGHT_BYTES_PER_STEP
+    kv_mean = KV_BYTES_PER_SLOT * float(kv_slots.mean()) if n_dec else 0.0
+    bytes_per_step = WEIGHT_BYTES_PER_STEP + kv_mean
     step_ms = dms / max(dsteps, 1)
     achieved = bytes_per_step / (step_ms / 1e3) / 1e9 if dsteps else 0.0
     peak, peak_src = peaks()
 
+    # ---- parity of the benchmarked recording against the reference's trace of its first 60 s
+    parity = None
+    gpath = os.path.join(ROOT, "tests", "golden", "synth_s60_oneshot.npz")
+    if os.path.exists(gpath) and args.seconds >= 60:
+        g = np.load(gpath)
+        ref = g["tokens"]; margin = g["top_val"][:, 0] - g["top_val"][:, 1]
+        n_cmp = min(len(ids), len(ref) - 40)              # the last positions of the 60 s trace see its right padding
+        bad = np.nonzero(ids[:n_cmp] != ref[:n_cmp])[0]
+        parity = {"compared_ids": int(n_cmp), "reference": "tests/golden/synth_s60_oneshot.npz (unmodified reference, oracle/ref_trace)",
+                  "first_mismatch": int(bad[0]) if bad.size else None,
+                  "reference_margin_at_mismatch": float(margin[bad[0]]) if bad.size else None}
+    parity_ok = bool(parity is not None and parity["first_mismatch"] is None)
+
+    # ---- several streams per weight pass on this GPU (N = 1 only: the scaling run keeps one stream per GPU)
+    ms_block = None
+    if world == 1 and not profiling and args.streams > 1:
+        B = args.streams
+        forks = [eng.fork() for _ in range(B - 1)]
+        engines = [eng] + forks
+
+        def batched_pass():
+            streams = [e.stream() for e in engines]
+            for s in streams:
+                s.set_deferred(1)
+                s.feed_device(d_pcm, pcm.size)
+            vb.streams_decode(streams)
+            for s in streams:
+                s.finish()
+            vb.streams_decode(streams)
+            out = [s.token_ids() for s in streams]
+            for s in streams:
+                s.close()
+            return out
+
+        batched_pass()                                         # warm-up (workspaces of the forks grow here)
+        j0 = eng.info()
+        b_ms, _, b_ids = timed(1, batched_pass)
+        j1 = eng.info()
+        b_steps = j1["total_decode_steps"] - j0["total_decode_steps"]
+        b_dms = j1["total_decode_kernel_ms"] - j0["total_decode_kernel_ms"]
+        b_step_ms = b_dms / max(b_steps, 1)
+        b_bytes = WEIGHT_BYTES_PER_STEP + B * kv_mean
+        ms_block = {"streams": B, "value": B * args.seconds / (b_ms / 1e3), "unit": "x real-time (aggregate over the streams of this GPU)",
+                    "per_stream": args.seconds / (b_ms / 1e3), "ms_per_pass": b_ms,
+                    "ids_equal_single_stream": bool(all(np.array_equal(x, ids) for x in b_ids)),
+                    "decode_ms_per_step": b_step_ms, "decoder_tok_s": B * b_steps / (b_dms / 1e3) if b_dms else None,
+                    "roofline": {"bound": "hbm", "achieved": b_bytes / (b_step_ms / 1e3) / 1e9 if b_steps else 0.0, "peak": peak, "unit": "GB/s",
+                                 "frac": (b_bytes / (b_step_ms / 1e3) / 1e9 / peak) if b_steps else 0.0, "bytes_per_step": b_bytes,
+                                 "note": "one weight pass (6.858 GB) + the f32 KV rows of every stream per step"},
+                    "api": "vox_cuda_ctx_fork + vox_cuda_stream_set_deferred + vox_cuda_streams_decode"}
+        for f in forks:
+            f.close()
+
+    # ---- one long recording, encoder sharded over the ranks (N > 1)
+    sharded = None
+    if world > 1 and not profiling:
+        sharded = sharded_encoder_leg(vb, eng, dist, rank, world, local, multi, args.sharded_seconds)
+
     if rank == 0:
         cpu = reference_sample(model, args.seconds) if (world == 1 and not profiling) else None
+        traffic, traffic_src = ncu_traffic()
         line = {
             "metric": "real-time factor (audio-s/wall-s)", "value": value, "unit": "x real-time", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": n_warm, "ms_per_step": dev_ms / args.steps,
@@ -272,28 +370,89 @@ def main():
             "dtype": "f32 activations x bf16 weights, f32 accumulate", "data": "synthetic",
             "config": {"workload": workload, "streams": world, "mel_frames": counts["mel_frames"],
                        "adapter_tokens": counts["adapter_tokens"], "decoder_steps": int(n_dec),
+                       "weights": "seeded synthetic checkpoint (no network for the real one; throughput is weight-agnostic)",
                        "l2_policy": "inputs larger than L2: every step streams 6.86 GB of weights (L2 = 126 MB)"},
             "decoder_tok_s": (dsteps / (dms / 1e3)) * world if dms else None,
             "decode_ms_per_step": step_ms,
             "encoder_positions_per_s": ((i_after["total_encoder_positions"] - i_before["total_encoder_positions"]) /
                                         max((i_after["total_encoder_ms"] - i_before["total_encoder_ms"]) / 1e3, 1e-9)),
+            "load_s": load_s,
             "gpu_launches": int(i_after["kernel_launches"] - i_before["kernel_launches"]),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "x real-time", "h2d_bytes_per_step": int(pcm.nbytes),
                     "d2h_bytes_per_step": int(4 * n_dec)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_STEP, "traffic_source": NCU_TRAFFIC_SOURCE,
-                         "kernel": "decoder step (26 layers of GEMV + attention + logits GEMV)",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "k_dec_v2<1>: persistent decode kernel, one step = 26 layers of GEMV + attention + logits GEMV",
                          "bytes_per_step": bytes_per_step, "peak_source": peak_src},
             "cpu_baseline": ({"value": cpu["rtf"], "unit": "x real-time", "cores": cpu["cores"], "kind": "reference",
-                              "sample": cpu["sample"], "decoder_tok_s": cpu["tok_s"]} if cpu else None),
+                              "sample": cpu["sample"], "decoder_tok_s": cpu["tok_s"], "extrapolated": True,
+                              "measured": cpu["measured"]} if cpu else None),
             "tokens_equal_between_legs": bool(np.array_equal(ids, ids2)),
+            "parity_prefix_ok": parity_ok, "parity_prefix": parity,
+            "multistream": ms_block,
+            "sharded_encoder": sharded,
         }
         print(json.dumps(line))
     eng.dev_free(d_pcm)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def sharded_encoder_leg(vb, eng, dist, rank, world, local, multi, seconds):
+    """One `seconds`-long recording: every rank encodes its slice (vox_cuda_encode_sharded, host C + NCCL), rank 0 also runs the
+    same call unsharded on a forked context and checks adapter rows + a decoded prefix.  Returns the JSON block (rank 0)."""
+    import torch
+    L = vb.lib()
+    fp = C.POINTER(C.c_float)
+    if rank == 0:
+        ensure_inputs(seconds)
+    dist.barrier()
+    _, pcm = ensure_inputs(seconds)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = (C.c_char * 128)()
+        assert L.vox_cuda_dist_unique_id(buf) == 0
+        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    uid = uid.cuda(local)
+    dist.broadcast(uid, 0)
+    raw = bytes(uid.cpu().tolist())
+    assert L.vox_cuda_dist_init(eng.ctx, rank, world, raw) == 0
+
+    def encode(ctx):
+        d_ad = C.c_void_p(); T = C.c_int(); P = C.c_int(); ms = C.c_double()
+        rc = L.vox_cuda_encode_sharded(ctx, pcm.ctypes.data_as(fp), pcm.size, C.byref(d_ad), C.byref(T), C.byref(P), C.byref(ms))
+        assert rc == 0
+        return d_ad, T.value, P.value, ms.value
+
+    encode(eng.ctx)                                            # warm-up
+    dist.barrier()
+    d_ad, T, P, ms = encode(eng.ctx)
+    ms_max = multi.reduce_max([ms], dist, torch.device("cuda", local))[0]
+    block = None
+    if rank == 0:
+        f = eng.fork()                                         # a context without a communicator: the same call, unsharded
+        encode(f.ctx)
+        d1, T1, P1, ms1 = encode(f.ctx)
+        a = np.empty((T, 3072), np.float32); b = np.empty((T1, 3072), np.float32)
+        L.vox_cuda_memcpy_d2h(eng.ctx, a.ctypes.data_as(C.c_void_p), d_ad, a.nbytes)
+        L.vox_cuda_memcpy_d2h(f.ctx, b.ctypes.data_as(C.c_void_p), d1, b.nbytes)
+        n_ids = 256
+        ids_s = np.zeros(n_ids, np.int32); ids_1 = np.zeros(n_ids, np.int32)
+        ip = C.POINTER(C.c_int)
+        g_s = L.vox_cuda_decode_adapter(eng.ctx, d_ad, T, ids_s.ctypes.data_as(ip), n_ids)
+        g_1 = L.vox_cuda_decode_adapter(f.ctx, d1, T1, ids_1.ctypes.data_as(ip), n_ids)
+        block = {"seconds": seconds, "positions": P, "adapter_tokens": T, "ranks": world,
+                 "encode_ms": ms_max, "encode_ms_1gpu": ms1, "speedup_vs_1": ms1 / ms_max, "efficiency": ms1 / ms_max / world,
+                 "positions_per_s": P / (ms_max / 1e3),
+                 "collective": "ncclSend/ncclRecv of the last 750 K and V rows to the right neighbour in every layer + one ncclAllGather of the adapter rows, on the engine's stream (host C, vb_dist.c)",
+                 "adapter_max_abs_diff_vs_unsharded": float(np.abs(a - b).max()) if T == T1 else None,
+                 "adapter_scale": float(np.abs(b).max()),
+                 "ids_prefix_equal_unsharded": bool(g_s == g_1 and np.array_equal(ids_s[:g_s], ids_1[:g_1])), "ids_prefix_len": int(g_s)}
+        f.close()
+    dist.barrier()
+    return block
 
 
 if __name__ == "__main__":

@@ -423,6 +423,20 @@ double vox_cuda_timer_stop_ms(vox_ctx_t *ctx);
 int vox_cuda_debug_copy_kv(vox_ctx_t *ctx, int layer, float *h_k, float *h_v);
 int vox_cuda_debug_copy_logits(vox_ctx_t *ctx, float *h_logits);
 
+/* ---- ONE long recording over the GPUs of a node: sequence-sharded encoder (vb_dist.c; BASELINE.json configs[4]) ----
+ * One process per GPU.  rank r owns a contiguous 4-aligned range of encoder positions (vox_cuda_shard_plan); per layer it
+ * sends its last 750 K/V rows to rank r+1 (ncclSend/ncclRecv on the ctx's stream, no host sync in the layer loop); adapter
+ * rows are all-gathered.  Exact: same per-row arithmetic as the unsharded encoder.  The decoder does not shard
+ * (autoregressive): one rank calls vox_cuda_decode_adapter.  The 128-byte NCCL id is created on one rank and handed to the
+ * others by the launcher.  world == 1 needs no NCCL and runs the same code unsharded. */
+int  vox_cuda_shard_plan(int n_positions, int world, int rank, int *p0, int *p1, int *halo_rows);
+int  vox_cuda_dist_unique_id(void *out128);
+int  vox_cuda_dist_init(vox_ctx_t *ctx, int rank, int world, const void *id128);
+void vox_cuda_dist_shutdown(vox_ctx_t *ctx);
+int  vox_cuda_encode_sharded(vox_ctx_t *ctx, const float *pcm, int n_samples, float **d_adapter_out, int *n_tokens,
+                             int *n_positions, double *encode_ms);
+int  vox_cuda_decode_adapter(vox_ctx_t *ctx, const float *d_adapter, int n_tokens, int *out_ids, int max_ids);
+
 /* Test hook for the error paths: the n-th device allocation from now on, and every later one, fails with an out-of-memory
  * error (n < 0: off).  With it vox_load returns NULL, vox_stream_init NULL, vox_stream_feed/flush/finish -1 -- the
  * reference's error returns (voxtral.c:132-158,1199-1200,1237) instead of a process abort. */

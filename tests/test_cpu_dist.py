@@ -72,6 +72,23 @@ def test_shard_plan_properties():
     assert min(b - a for a, b in sh.plan_shards(180196, 8)) >= 22520
 
 
+def test_c_shard_plan_equals_the_python_plan():
+    """vox_cuda_shard_plan (host C, what vox_cuda_encode_sharded uses on the GPU box) == sharded.plan_shards / halo_rows."""
+    import ctypes as C
+    import vbload
+    sh = vbload.load_submodule("sharded")
+    L = vbload.load().lib()
+    L.vox_cuda_shard_plan.argtypes = [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+    for P in (0, 3, 748, 1696, 3196, 30196, 180196, 180199):
+        for w in (1, 2, 3, 4, 8):
+            plan = sh.plan_shards(P, w)
+            for r in range(w):
+                a, b, h = C.c_int(), C.c_int(), C.c_int()
+                assert L.vox_cuda_shard_plan(P, w, r, C.byref(a), C.byref(b), C.byref(h)) == 0
+                assert (a.value, b.value) == plan[r] and h.value == sh.halo_rows(plan[r][0])
+    assert L.vox_cuda_shard_plan(100, 2, 2, None, None, None) == -1
+
+
 def _halo_worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     import vbload

@@ -1,5 +1,6 @@
-"""Sequence-sharded encoder (NCCL K/V halo + adapter all-gather) == single-GPU pipeline.  Needs >= 2 GPUs; on a 1-GPU box
-the unsharded run of the same layer API is still checked against the streaming API."""
+"""Sequence-sharded encoder in host C (vb_dist.c: NCCL K/V halo + adapter all-gather) == single-GPU pipeline.  Needs >= 2
+GPUs; on a 1-GPU box the unsharded run of the same call (own-rows conv stem, split layers, vox_cuda_decode_adapter) is still
+checked against the streaming API."""
 import json
 import os
 import subprocess
@@ -21,7 +22,7 @@ def _run(nproc, seconds):
     return json.loads(line)
 
 
-def test_layer_api_matches_stream_api_single_gpu():
+def test_sharded_call_unsharded_matches_stream_api_single_gpu():
     out = _run(1, 8)
     assert out["tokens_equal_stream_api"] and out["adapter_max_abs_diff_vs_unsharded"] == 0.0
 

@@ -187,7 +187,6 @@ def test_60s_oneshot_matches_reference(engine):
     assert ids[:360].tolist() == g30["tokens"][:360].tolist()
 
 
-@pytest.mark.skipif(not os.environ.get("VOX_TEST_PENDING"), reason="fixture generated after the round's GPU budget was spent; not yet run on a B200")
 def test_live_feeding_100ms_matches_reference(engine):
     """main.c's live mode in miniature: 0.1-s feeds with a 0.1-s processing interval -- after the first chunk every encoder call
     sees about 10 mel frames (5 positions), and tokens leave the queue one or two per feed.  Per-feed counts must match."""
@@ -208,7 +207,6 @@ def test_live_feeding_100ms_matches_reference(engine):
     check_against(g, ids, b"".join(pieces))
 
 
-@pytest.mark.skipif(not os.environ.get("VOX_TEST_PENDING"), reason="fixture generated after the round's GPU budget was spent; not yet run on a B200")
 def test_delay_2400ms_matches_reference(engine):
     """The largest delay the API accepts: 30 delay tokens, a 63-row prompt, 41 tokens of flush padding."""
     g = golden("synth_s2_delay2400")

@@ -6,5 +6,5 @@ package is only the ctypes view of its C ABI (``include/voxtral_b200.h``) that t
 with ``vbload.load()`` (repo root) rather than a plain ``import``.
 """
 from .binding import (  # noqa: F401
-    LIB_PATH, PKG_DIR, REPO_ROOT, Engine, Stream, build, lib, declared_symbols, have_gpu,
+    LIB_PATH, PKG_DIR, REPO_ROOT, Engine, Stream, build, lib, declared_symbols, have_gpu, streams_decode,
 )

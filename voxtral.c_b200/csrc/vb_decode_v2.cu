@@ -64,7 +64,7 @@ struct V2Args {
     unsigned int *bar;                         /* [0] grid barrier, [16..23] attention tickets, [32] error word */
     unsigned int *ctr;                         /* [n_steps][V2_SUBPHASES] chunk counters of the dynamic phases */
     VbDecState *st_out;                        /* [nb] */
-    int nb, n_steps, inflight_max, dynamic, verify;
+    int nb, n_steps, inflight_max, dynamic, verify, dbg;
     long long *prof; int prof_step;
 };
 
@@ -125,21 +125,25 @@ __device__ __forceinline__ void v2_static_rows(int total, int unit, int &r0, int
 /* ------------------------------------------------------------------ producer */
 struct V2Producer {
     V2Smem *sm; uint8_t *slots; int *err; uint32_t it, landed; int inflight_max; bool dead;
-    long long n_chunks, t_wait;
+    long long n_chunks, t_wait, t_cap;       /* chunks issued; cycles waiting for a free slot / for the in-flight cap */
 
     __device__ __forceinline__ bool acquire() {          /* a free slot, and room under the in-flight cap */
         const int s = (int)(it % V2_SLOTS);
         const uint32_t par = (it / V2_SLOTS) & 1u;
         long long t0 = 0;
+        const long long ta = clock64();
         while (!mbar_try_wait(&sm->empty[s], par ^ 1u)) {
             if (sm->abort_flag) { dead = true; return false; }
             spin_guard(t0, err, 2);
         }
+        const long long tb = clock64();
+        t_wait += tb - ta;
         while (it - landed >= (uint32_t)inflight_max) {
             const uint32_t j = landed;
             if (mbar_try_wait(&sm->full[j % V2_SLOTS], (j / V2_SLOTS) & 1u)) landed++;
             else { if (sm->abort_flag) { dead = true; return false; } spin_guard(t0, err, 5); }
         }
+        t_cap += clock64() - tb;
         return true;
     }
     __device__ __forceinline__ void push_rows(const V2Phase &f, int row0, int nrows) {
@@ -180,7 +184,8 @@ struct V2Producer {
 __device__ void v2_producer(V2Smem *sm, uint8_t *slots, const V2Args &a) {
     V2Producer P;
     P.sm = sm; P.slots = slots; P.err = (int *)(a.bar + 32); P.it = 0; P.landed = 0; P.inflight_max = a.inflight_max; P.dead = false;
-    P.n_chunks = 0; P.t_wait = 0;
+    P.n_chunks = 0; P.t_wait = 0; P.t_cap = 0;
+    const long long t_begin = clock64();
     for (int step = 0; step < a.n_steps && !P.dead; step++) {
         unsigned int *ctr = a.ctr + (size_t)step * V2_SUBPHASES;
         for (int layer = 0; layer < VOX_DEC_LAYERS && !P.dead; layer++) {
@@ -193,6 +198,10 @@ __device__ void v2_producer(V2Smem *sm, uint8_t *slots, const V2Args &a) {
             P.run_phase(v2_phase(a.p, layer, 3, 2), nullptr, 0);
         }
         P.run_phase(v2_phase(a.p, 0, 4, 0), ctr + VOX_DEC_LAYERS * 4, a.dynamic);
+    }
+    if (a.prof) {
+        long long *pp = a.prof + (size_t)blockIdx.x * V2_PROF_SLOTS + V2_PROF_SLOTS - 8;
+        pp[0] = P.n_chunks; pp[1] = P.t_wait; pp[2] = P.t_cap; pp[3] = clock64() - t_begin;
     }
     /* every bulk copy that was issued must land before the CTA may exit (shared memory is its target) */
     while (P.landed < P.it) {
@@ -290,59 +299,90 @@ __device__ __forceinline__ void v2_dot8(const uint4 w, const V2X<NB> &x, float (
 
 /* Consume the chunks of one (sub)phase from the ring until the producer's end marker.
  * NT = threads that own a 16-byte column of the row segment (384 for 3072-wide, 256 for 2048-wide segments).
- * epi(row, b, value, lane, valid) runs in the last consumer warp, lane = (row - row0) * NB + b. */
+ * Partial sums of 16 (row, column) pairs are reduced together -- 4 chunks x 4 rows for one column, 2 chunks for two columns,
+ * one chunk for four, half a chunk for eight -- so the cost of a reduction (15 shuffles, one shared-memory pass, one named
+ * barrier) is the same per 16 outputs whatever NB is, and a slot is released as soon as its rows are in the accumulators.
+ * epi(row, b, value, lane, valid) runs in the last consumer warp; lane = (chunk * 4 + row_in_chunk) * NB + b. */
 template <int NB, typename Epi>
 __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uint32_t &it, int seg_bytes, int NT,
-                                           const V2X<NB> &x, int &redbuf, int *err, Epi epi) {
-    constexpr int RG = NB >= 4 ? 2 : V2_RC;           /* rows per reduction group (register budget: 128 per thread) */
-    constexpr int R = RG * NB;                         /* values reduced together */
-    constexpr int LG = V2Log2<R>::v;
+                                           const V2X<NB> &x, int &redbuf, int *err, long long &t_stall, int dbg, Epi epi) {
+    constexpr int CPR = NB == 1 ? 4 : NB == 2 ? 2 : 1;     /* chunks per reduction */
+    constexpr int HALVES = NB == 8 ? 2 : 1;                /* NB = 8: a chunk's 32 values are reduced as two halves (registers) */
+    constexpr int RH = V2_RC / HALVES;                     /* rows per half */
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const bool active = t < NT;
-    for (;;) {
-        const int s = (int)(it % V2_SLOTS);
-        const uint32_t par = (it / V2_SLOTS) & 1u;
-        long long t0 = 0;
-        while (!mbar_try_wait(&sm->full[s], par)) spin_guard(t0, err, 3);
-        const int nrows = sm->meta_nrows[s], row0 = sm->meta_row0[s];
-        const uint8_t *base = slots + (size_t)s * V2_SLOT_BYTES + (size_t)t * 16;
-        if (nrows > 0) {
+    bool end = false;
+    while (!end) {
+        float acc[16];
 #pragma unroll
-            for (int h = 0; h < V2_RC / RG; h++) {
-                float acc[R];
+        for (int i = 0; i < 16; i++) acc[i] = 0.f;
+        int row0s[CPR], nrs[CPR], got = 0;
 #pragma unroll
-                for (int i = 0; i < R; i++) acc[i] = 0.f;
-                if (active) {
-                    uint4 w[RG];
+        for (int c = 0; c < CPR; c++) {
+            row0s[c] = 0; nrs[c] = 0;
+            if (end) continue;
+            const int s = (int)(it % V2_SLOTS);
+            const uint32_t par = (it / V2_SLOTS) & 1u;
+            if (!mbar_try_wait(&sm->full[s], par)) {
+                const long long tw = clock64();
+                long long t0 = 0;
+                while (!mbar_try_wait(&sm->full[s], par)) spin_guard(t0, err, 3);
+                t_stall += clock64() - tw;
+            }
+            const int nrows = sm->meta_nrows[s];
+            row0s[c] = sm->meta_row0[s]; nrs[c] = nrows;
+            if (nrows == 0) end = true;
+            else {
+                got++;
+                const uint8_t *base = slots + (size_t)s * V2_SLOT_BYTES + (size_t)t * 16;
 #pragma unroll
-                    for (int r = 0; r < RG; r++)
-                        w[r] = (h * RG + r < nrows) ? *reinterpret_cast<const uint4 *>(base + (size_t)(h * RG + r) * seg_bytes) : make_uint4(0u, 0u, 0u, 0u);
+                for (int h = 0; h < HALVES; h++) {
+                    if (active && !(dbg & 1)) {
+                        uint4 w[RH];
 #pragma unroll
-                    for (int r = 0; r < RG; r++) {
-                        float a[NB];
+                        for (int r = 0; r < RH; r++)
+                            w[r] = (h * RH + r < nrows) ? *reinterpret_cast<const uint4 *>(base + (size_t)(h * RH + r) * seg_bytes) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                        for (int b = 0; b < NB; b++) a[b] = 0.f;
-                        v2_dot8<NB>(w[r], x, a);
+                        for (int r = 0; r < RH; r++) {
+                            float a[NB];
 #pragma unroll
-                        for (int b = 0; b < NB; b++) acc[r * NB + b] = a[b];
+                            for (int b = 0; b < NB; b++) a[b] = 0.f;
+                            v2_dot8<NB>(w[r], x, a);
+#pragma unroll
+                            for (int b = 0; b < NB; b++) acc[(HALVES == 2 ? 0 : c * V2_RC * NB) + r * NB + b] = a[b];
+                        }
+                    }
+                    if (HALVES == 2 && !(dbg & 2)) {        /* NB = 8: reduce this half now, lanes 16h..16h+15 of the result row */
+                        const float tot = v2_transpose_reduce<16>(acc, lane);
+                        if (!(lane & 1)) sm->red[redbuf][warp][h * 16 + (lane >> 1)] = tot;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) acc[i] = 0.f;
                     }
                 }
-                const float tot = v2_transpose_reduce<R>(acc, lane);
-                if ((lane & ((32 >> LG) - 1)) == 0) sm->red[redbuf][warp][h * R + (lane >> (5 - LG))] = tot;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm->empty[s]);     /* the rows are in registers: the slot can be refilled */
+            it++;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm->empty[s]);
-        it++;
-        if (nrows == 0) break;
+        if (got == 0) break;
+        if (dbg & 2) continue;
+        if (HALVES == 1) {
+            const float tot = v2_transpose_reduce<16>(acc, lane);
+            if (!(lane & 1)) sm->red[redbuf][warp][lane >> 1] = tot;
+        }
         v2_bar();
         if (warp == V2_CW - 1) {
+            constexpr int NV = 16 * HALVES;                 /* values in this reduction: lane < NV */
             float sum = 0.f;
-            if (lane < V2_RC * NB) {
+            if (lane < NV) {
 #pragma unroll
                 for (int wv = 0; wv < V2_CW; wv++) sum += sm->red[redbuf][wv][lane];
             }
-            epi(row0 + lane / NB, lane % NB, sum, lane, lane < V2_RC * NB && lane / NB < nrows);
+            const int c = lane / (V2_RC * NB), r = (lane / NB) % V2_RC;
+            int row0 = row0s[0], nr = nrs[0];
+#pragma unroll
+            for (int k = 1; k < CPR; k++) if (c == k) { row0 = row0s[k]; nr = nrs[k]; }
+            epi(row0 + r, lane % NB, sum, lane, lane < NV && r < nr);
         }
         redbuf ^= 1;
     }
@@ -571,6 +611,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
     uint32_t it = 0;
     unsigned int gen = 0;
     int redbuf = 0, prof_n = 0;
+    long long t_stall = 0;                                     /* cycles this thread waited for weight chunks (whole launch) */
     int my_r0, my_r1;                                          /* residual-stream rows this CTA owns (static wo / w2 partition) */
     v2_static_rows(VOX_DEC_DIM, 1, my_r0, my_r1);
 
@@ -617,7 +658,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 v2_rmsnorm<NB>(x, nw, sub == 3 ? p.ada + (size_t)layer * VOX_DEC_DIM : nullptr, sm);
             }
             const float *inv_freq = p.inv_freq;
-            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, err, [&](int row, int b, float v, int, bool valid) {
+            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, err, t_stall, a.dbg, [&](int row, int b, float v, int, bool valid) {
                 const float other = __shfl_xor_sync(0xffffffffu, v, NB);    /* row ^ 1 of the same column: RoPE pair / (gate, up) pair */
                 if (!valid) return;
                 switch (sub) {
@@ -706,6 +747,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
         V2PROF();
     }
     if (tid == 0) {
+        if (a.prof) a.prof[(size_t)blockIdx.x * V2_PROF_SLOTS + V2_PROF_SLOTS - 1] = t_stall;
         sm->abort_flag = 1;                                            /* the producer may be ahead of an early exit (EOS) */
         if (blockIdx.x == 0) {
             for (int b = 0; b < a.nb; b++) {
@@ -787,6 +829,10 @@ static void v2_prof_report(VbEngine *e, const V2Args &a) {
         for (int k = 0; k < 10; k++) { fprintf(stderr, " %s=%.0f", names[k], sum[k] / (VOX_DEC_LAYERS - 2)); tot += sum[k]; }
         fprintf(stderr, " | layer=%.0f | logits=%lld bar=%lld feedback=%lld step=%lld\n", tot / (VOX_DEC_LAYERS - 2),
                 t[26 * 10 + 1] - t[26 * 10], t[26 * 10 + 2] - t[26 * 10 + 1], t[26 * 10 + 3] - t[26 * 10 + 2], t[26 * 10 + 3] - t[0]);
+        const long long *q = t + V2_PROF_SLOTS - 8;
+        fprintf(stderr, "[v2 prof nb=%d] cta %3d whole launch: producer %lld chunks in %lld cycles (%.0f/chunk; waiting for a free slot %.0f, for the in-flight cap %.0f per chunk); "
+                        "consumer thread 0 waited %.0f cycles per chunk for data\n", a.nb, ctas[ci], q[0], q[3], (double)q[3] / (double)(q[0] ? q[0] : 1),
+                (double)q[1] / (double)(q[0] ? q[0] : 1), (double)q[2] / (double)(q[0] ? q[0] : 1), (double)t[V2_PROF_SLOTS - 1] / (double)(q[0] ? q[0] : 1));
     }
     free(h);
 }
@@ -819,6 +865,7 @@ extern "C" int vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb,
     if (a.inflight_max < 1) a.inflight_max = 1;
     if (a.inflight_max > V2_SLOTS) a.inflight_max = V2_SLOTS;
     a.dynamic = (ev = getenv("VOX_CUDA_V2_DYNAMIC")) ? atoi(ev) : 1;
+    a.dbg = (ev = getenv("VOX_CUDA_V2_DBG")) ? atoi(ev) : 0;     /* diagnostics only (results are wrong): 1 = no FMAs, 2 = no reductions/epilogues */
     a.prof = NULL; a.prof_step = -1;
     if ((ev = getenv("VOX_CUDA_V2_PROF")) && n_steps > atoi(ev)) {
         if (!s->prof) { const size_t wb = lead->weight_bytes; s->prof = (long long *)vb_dev_alloc_owned(lead, (size_t)lead->sm_count * V2_PROF_SLOTS * 8); lead->weight_bytes = wb; }

@@ -33,8 +33,10 @@
 #define VB_DEC_QKV   (VB_DEC_Q + 2 * VB_DEC_KV)                        /* 6144 */
 #define VB_KV_SLOTS  VOX_DEC_WINDOW                                    /* 8192 */
 #define VB_TOKEN_EOS 2
-#define VB_WS_SLOTS  24   /* 0-11: model blocks (see vb_encoder.cu), 12-23: stream pipeline */
+#define VB_WS_SLOTS  32   /* 0-11: model blocks (see vb_encoder.cu), 12-19: stream pipeline (vb_stream.c), then: */
 #define VB_WS_ALT    20   /* 8 floats: result of the alternatives kernel (vb_decode.cu) */
+#define VB_WS_DIST_X 21   /* 21-23: sharded encoder (vb_dist.c): own rows, K and V with halo */
+#define VB_WS_GEMM_PLANES 24  /* bf16 split planes of the tcgen05 GEMM (vb_gemm_tc.cu) */
 
 /* Error boundary.  Inside the library a failed CUDA call (cudaMalloc out of memory, a launch error...) reports through
  * vb_cuda_fail().  Public entry points that have an error return in the reference -- vox_load -> NULL (voxtral.c:132-158),
@@ -140,6 +142,8 @@ typedef struct VbEngine {
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
     VbV2Scratch v2; int v2_checked, v2_ok;
+    void *dist;                                 /* VbDist* (vb_dist.c): NCCL communicator of the sequence-sharded encoder */
+    float *d_dist_adapter; int dist_adapter_cap;   /* gathered adapter rows of vox_cuda_encode_sharded */
 
     /* ---- M>1 scratch (prefill / encoder / adapter) ---- */
     float *ws[VB_WS_SLOTS]; size_t ws_bytes[VB_WS_SLOTS];         /* grow-on-demand workspaces */
@@ -218,6 +222,7 @@ void vb_d2h_sync(VbEngine *e, void *dst, const void *src, size_t bytes);
 void vb_sync(VbEngine *e);
 void vb_build_prompt_dev(VbEngine *e, float *d_out, const float *d_adapter, int n, int bos, int pad);
 void vb_conv_stem_full_dev(VbEngine *e, const float *d_mel, int mel_frames, float *d_out, int *out_len);
+void vb_conv_stem_range_dev(VbEngine *e, const float *d_mel, int mel_frames, int p0, int p1, float *d_out);
 void vb_gemv_bf16_dev(VbEngine *e, float *y, const float *x, const uint16_t *W, const float *bias, int K, int N);
 
 #ifdef __cplusplus

@@ -266,7 +266,7 @@ void vb_gemm_tc(VbEngine *e, const float *A, int lda, const uint16_t *W, const f
                 int M, int N, int K, int epi) {
     static int attr_done = 0;
     const int nsplit = vb_gemm_nsplit();
-    uint16_t *planes = (uint16_t *)vb_ws(e, 20, (size_t)nsplit * M * K * 2 + 256);
+    uint16_t *planes = (uint16_t *)vb_ws(e, VB_WS_GEMM_PLANES, (size_t)nsplit * M * K * 2 + 256);
     long long quads = ((long long)M * K + 3) / 4;
     k_split_planes<<<(int)((quads + 255) / 256), 256, 0, e->stream>>>(A, lda, M, K, nsplit, planes);
     CUtensorMap tmA, tmW;

@@ -238,9 +238,9 @@ static int load_decoder(VbEngine *e, safetensors_file_t *sf) {
 }
 
 vox_ctx_t *vox_load(const char *model_dir) {
-    VbEngine *e = calloc(1, sizeof *e);
+    VbEngine *volatile e = calloc(1, sizeof *e);           /* volatile: read after a longjmp back into this frame */
     if (!e) return NULL;
-    vox_ctx_t *ctx = &e->pub;
+    vox_ctx_t *volatile ctx = &e->pub;
     snprintf(ctx->model_dir, sizeof ctx->model_dir, "%s", model_dir);
     ctx->delay_tokens = 6;
     ctx->use_bf16 = 1;
@@ -299,6 +299,7 @@ vox_ctx_t *vox_cuda_ctx_fork(vox_ctx_t *parent) {
     memset(&e->v2, 0, sizeof e->v2);
     memset(e->ws, 0, sizeof e->ws); memset(e->ws_bytes, 0, sizeof e->ws_bytes);
     e->d_enc_tail_k = e->d_enc_tail_v = NULL; e->enc_tail_len = 0;
+    e->dist = NULL; e->d_dist_adapter = NULL; e->dist_adapter_cap = 0;
     e->launches = 0; e->last_decode_ms = e->last_encoder_ms = e->last_mel_ms = 0; e->last_decode_steps = e->last_encoder_positions = 0;
     e->total_decode_ms = e->total_encoder_ms = 0; e->total_decode_steps = e->total_encoder_positions = 0;
     vox_ctx_t *c = &e->pub;
@@ -338,6 +339,7 @@ void vox_free(vox_ctx_t *ctx) {
     FREE0(ctx->ada_scale);
 #undef FREE0
     vb_decoder_free(e);
+    vox_cuda_dist_shutdown(ctx);
     vb_device_shutdown(e);
     if (ctx->safetensors) safetensors_close((safetensors_file_t *)ctx->safetensors);
     free(e);

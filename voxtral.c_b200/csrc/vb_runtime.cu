@@ -76,6 +76,7 @@ extern "C" void vb_device_shutdown(VbEngine *e) {
     free(e->owned); e->owned = NULL; e->n_owned = 0;
     if (!e->parent) { free(e->mirrors); e->mirrors = NULL; e->n_mirrors = 0; }
     for (int i = 0; i < VB_WS_SLOTS; i++) { cudaFree(e->ws[i]); e->ws[i] = NULL; e->ws_bytes[i] = 0; }
+    cudaFree(e->d_dist_adapter); e->d_dist_adapter = NULL; e->dist_adapter_cap = 0;
     if (e->step_graph_ready) cudaGraphExecDestroy(e->step_graph);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->ev_user0); cudaEventDestroy(e->ev_user1);

@@ -456,7 +456,7 @@ static void run_decoder(vox_stream_t *s) {
 /* ---------------------------------------------------------------- public stream API */
 vox_stream_t *vox_stream_init(vox_ctx_t *ctx) {
     if (!ctx) return NULL;
-    vox_stream_t *s = calloc(1, sizeof *s);
+    vox_stream_t *volatile s = calloc(1, sizeof *s);
     if (!s) return NULL;
     VB_API_GUARD({ fprintf(stderr, "vox_stream_init: device allocation failed\n"); return NULL; });
     s->ctx = ctx; s->e = vb_engine(ctx);

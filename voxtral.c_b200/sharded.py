@@ -1,4 +1,7 @@
-"""Sequence-sharded encoding of ONE long recording over the GPUs of a node (BASELINE.json configs[4]).
+"""Sequence-sharded encoding of ONE long recording over the GPUs of a node (BASELINE.json configs[4]) -- the PROTOTYPE and
+the CPU-testable mirror of the host logic.  The product path is host C: csrc/vb_dist.c (vox_cuda_encode_sharded, NCCL on the
+engine's stream, no host sync in the layer loop); tests/test_cpu_dist.py checks that its shard plan equals plan_shards() here
+and runs this module's exchange schedule over gloo.
 
 Exact, not approximate: rank r owns a contiguous range of encoder positions (aligned to the 4x adapter groups).  In every
 layer all ranks first compute q/k/v (+RoPE at GLOBAL positions) for their own rows, then rank r sends its last 750 K/V
@@ -97,6 +100,7 @@ def sharded_encode(vb, eng, pcm, dist, rank, world):
     del x_all
     kb = torch.zeros((h + M, 2048), dtype=torch.float32, device=dev)
     vv = torch.zeros((h + M, 2048), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()        # the library writes these buffers on ITS stream: the memsets on torch's stream must have landed
     for layer in range(32):
         L.vox_cuda_encoder_layer_qkv(ctx, layer, x.data_ptr(), M, p0, kb.data_ptr(), vv.data_ptr(), h)
         L.vox_cuda_sync(ctx)
@@ -108,6 +112,7 @@ def sharded_encode(vb, eng, pcm, dist, rank, world):
     L.vox_cuda_encoder_final_norm(ctx, x.data_ptr(), M)
     T_max = max((b - a) // 4 for a, b in shards)
     a_r = torch.zeros((T_max, 3072), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
     L.vox_cuda_adapter(ctx, x.data_ptr(), M, a_r.data_ptr())
     L.vox_cuda_sync(ctx)
     adapter = gather_adapter(dist, world, shards, a_r)
