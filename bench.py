@@ -376,7 +376,7 @@ def main():
             "decode_ms_per_step": step_ms,
             "encoder_positions_per_s": ((i_after["total_encoder_positions"] - i_before["total_encoder_positions"]) /
                                         max((i_after["total_encoder_ms"] - i_before["total_encoder_ms"]) / 1e3, 1e-9)),
-            "load_s": load_s,
+            "load_s": load_s, "load_s_library": eng.info()["load_ms"] / 1e3,
             "gpu_launches": int(i_after["kernel_launches"] - i_before["kernel_launches"]),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "x real-time", "h2d_bytes_per_step": int(pcm.nbytes),

@@ -377,6 +377,7 @@ typedef struct {
     long long total_decode_steps;
     double total_encoder_ms;             /* cumulative host-observed time of encoder+adapter passes */
     long long total_encoder_positions;
+    double load_ms;                      /* wall time of vox_load (checkpoint -> HBM) */
 } vox_cuda_info_t;
 int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out);
 const char *vox_cuda_version(void);

@@ -38,7 +38,7 @@ class CudaInfo(C.Structure):
                 ("last_decode_steps", C.c_int), ("last_encoder_kernel_ms", C.c_double),
                 ("last_encoder_positions", C.c_int), ("last_mel_kernel_ms", C.c_double),
                 ("total_decode_kernel_ms", C.c_double), ("total_decode_steps", C.c_longlong),
-                ("total_encoder_ms", C.c_double), ("total_encoder_positions", C.c_longlong)]
+                ("total_encoder_ms", C.c_double), ("total_encoder_positions", C.c_longlong), ("load_ms", C.c_double)]
 
 
 def lib():

@@ -81,6 +81,13 @@ struct V2Smem {
     volatile int abort_flag, is_last;
 };
 
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
 __device__ __forceinline__ void v2_bar() { asm volatile("bar.sync 1, %0;" :: "n"(V2_CONS) : "memory"); }
 
 __device__ __forceinline__ void v2_grid_barrier(unsigned int *bar, unsigned int &gen, int *err) {
@@ -123,92 +130,96 @@ __device__ __forceinline__ void v2_static_rows(int total, int unit, int &r0, int
 }
 
 /* ------------------------------------------------------------------ producer */
-struct V2Producer {
-    V2Smem *sm; uint8_t *slots; int *err; uint32_t it, landed; int inflight_max; bool dead;
-    long long n_chunks, t_wait, t_cap;       /* chunks issued; cycles waiting for a free slot / for the in-flight cap */
+/* ONE thread per CTA.  It is latency bound by construction (every chunk is a chain of try_wait -> meta -> expect_tx -> bulk copy),
+ * so all of its state lives in registers and there is a single copy of the per-chunk code: a flat loop over the (sub)phases.
+ * (A first version kept the state in a struct handed to a noinline function: ~30 local-memory accesses per chunk made the
+ * producer, not HBM, the bottleneck at 17 B/cycle/SM.) */
+__device__ void v2_producer(V2Smem *sm, uint8_t *slots, const V2Args &a) {
+    int *err = (int *)(a.bar + 32);
+    uint32_t it = 0, landed = 0;
+    const uint32_t inflight_max = (uint32_t)a.inflight_max;
+    bool dead = false;
+    long long n_chunks = 0, t_wait = 0, t_cap = 0;
+    const bool prof = a.prof != nullptr;
+    const long long t_begin = clock64();
 
-    __device__ __forceinline__ bool acquire() {          /* a free slot, and room under the in-flight cap */
+    /* a free slot, and room under the in-flight cap; false = the consumers left (EOS): stop */
+    auto acquire = [&]() -> bool {
         const int s = (int)(it % V2_SLOTS);
         const uint32_t par = (it / V2_SLOTS) & 1u;
         long long t0 = 0;
-        const long long ta = clock64();
+        long long ta = 0;
+        if (prof) ta = clock64();
         while (!mbar_try_wait(&sm->empty[s], par ^ 1u)) {
             if (sm->abort_flag) { dead = true; return false; }
             spin_guard(t0, err, 2);
         }
-        const long long tb = clock64();
-        t_wait += tb - ta;
-        while (it - landed >= (uint32_t)inflight_max) {
-            const uint32_t j = landed;
-            if (mbar_try_wait(&sm->full[j % V2_SLOTS], (j / V2_SLOTS) & 1u)) landed++;
+        long long tb = 0;
+        if (prof) { tb = clock64(); t_wait += tb - ta; }
+        while (it - landed >= inflight_max) {
+            if (mbar_try_wait(&sm->full[landed % V2_SLOTS], (landed / V2_SLOTS) & 1u)) landed++;
             else { if (sm->abort_flag) { dead = true; return false; } spin_guard(t0, err, 5); }
         }
-        t_cap += clock64() - tb;
+        if (prof) t_cap += clock64() - tb;
         return true;
-    }
-    __device__ __forceinline__ void push_rows(const V2Phase &f, int row0, int nrows) {
-        if (dead || !acquire()) return;
-        const int s = (int)(it % V2_SLOTS);
-        sm->meta_row0[s] = row0; sm->meta_nrows[s] = nrows;
-        uint8_t *dst = slots + (size_t)s * V2_SLOT_BYTES;
-        const uint8_t *src = f.W + (size_t)row0 * f.row_stride + f.col_off;
-        mbar_expect_tx(&sm->full[s], (uint32_t)(nrows * f.seg_bytes));
-        if (f.seg_bytes == f.row_stride) bulk_g2s(dst, src, (uint32_t)(nrows * f.seg_bytes), &sm->full[s]);
-        else for (int r = 0; r < nrows; r++) bulk_g2s(dst + (size_t)r * f.seg_bytes, src + (size_t)r * f.row_stride, (uint32_t)f.seg_bytes, &sm->full[s]);
-        it++; n_chunks++;
-    }
-    __device__ __forceinline__ void push_marker() {      /* "this CTA has no more rows in this phase" */
-        if (dead || !acquire()) return;
-        const int s = (int)(it % V2_SLOTS);
-        sm->meta_row0[s] = 0; sm->meta_nrows[s] = 0;
-        mbar_arrive(&sm->full[s]);
-        it++;
-    }
-    __device__ __noinline__ void run_phase(const V2Phase &f, unsigned int *ctr, int dynamic) {
-        if (f.dyn && dynamic) {
-            const unsigned int n = (unsigned int)(f.total_rows / V2_RC);
-            unsigned int g0 = atomicAdd(ctr, 1u), g1 = atomicAdd(ctr, 1u), g2 = atomicAdd(ctr, 1u);
-            while (g0 < n && !dead) {
-                push_rows(f, (int)g0 * V2_RC, V2_RC);
-                g0 = g1; g1 = g2; g2 = atomicAdd(ctr, 1u);
-            }
-        } else {
-            int r0, r1;
-            v2_static_rows(f.total_rows, f.dyn ? V2_RC : 1, r0, r1);
-            for (int r = r0; r < r1 && !dead; r += V2_RC) push_rows(f, r, min(V2_RC, r1 - r));
-        }
-        push_marker();
-    }
-};
+    };
 
-__device__ void v2_producer(V2Smem *sm, uint8_t *slots, const V2Args &a) {
-    V2Producer P;
-    P.sm = sm; P.slots = slots; P.err = (int *)(a.bar + 32); P.it = 0; P.landed = 0; P.inflight_max = a.inflight_max; P.dead = false;
-    P.n_chunks = 0; P.t_wait = 0; P.t_cap = 0;
-    const long long t_begin = clock64();
-    for (int step = 0; step < a.n_steps && !P.dead; step++) {
-        unsigned int *ctr = a.ctr + (size_t)step * V2_SUBPHASES;
-        for (int layer = 0; layer < VOX_DEC_LAYERS && !P.dead; layer++) {
-            P.run_phase(v2_phase(a.p, layer, 0, 0), ctr + layer * 4 + 0, a.dynamic);
-            P.run_phase(v2_phase(a.p, layer, 1, 0), nullptr, 0);
-            P.run_phase(v2_phase(a.p, layer, 1, 1), nullptr, 0);
-            P.run_phase(v2_phase(a.p, layer, 2, 0), ctr + layer * 4 + 2, a.dynamic);
-            P.run_phase(v2_phase(a.p, layer, 3, 0), nullptr, 0);
-            P.run_phase(v2_phase(a.p, layer, 3, 1), nullptr, 0);
-            P.run_phase(v2_phase(a.p, layer, 3, 2), nullptr, 0);
+    const int n_sub_total = a.n_steps * (VOX_DEC_LAYERS * 7 + 1);
+#pragma unroll 1
+    for (int flat = 0; flat < n_sub_total && !dead; flat++) {
+        const int step = flat / (VOX_DEC_LAYERS * 7 + 1), idx = flat - step * (VOX_DEC_LAYERS * 7 + 1);
+        const int layer = idx / 7;
+        const int sub = layer == VOX_DEC_LAYERS ? 7 : idx - layer * 7;
+        /* sub 0 QKV | 1,2 wo blocks | 3 w1|w3 | 4,5,6 w2 blocks | 7 logits */
+        const int ph = sub == 0 ? 0 : sub <= 2 ? 1 : sub == 3 ? 2 : sub <= 6 ? 3 : 4;
+        const int part = ph == 1 ? sub - 1 : ph == 3 ? sub - 4 : 0;
+        const V2Phase f = v2_phase(a.p, layer == VOX_DEC_LAYERS ? 0 : layer, ph, part);
+        const bool dyn = f.dyn && a.dynamic;
+        unsigned int *ctr = a.ctr + (size_t)step * V2_SUBPHASES + (ph == 4 ? VOX_DEC_LAYERS * 4 : layer * 4 + ph);
+        /* chunk source: dynamic = ids from the phase's global counter, three grabs ahead; static = this CTA's row range */
+        unsigned int g0 = 0, g1 = 0, g2 = 0;
+        int r = 0, r1 = 0;
+        const unsigned int n_dyn = (unsigned int)(f.total_rows / V2_RC);
+        if (dyn) { g0 = atomicAdd(ctr, 1u); g1 = atomicAdd(ctr, 1u); g2 = atomicAdd(ctr, 1u); }
+        else v2_static_rows(f.total_rows, f.dyn ? V2_RC : 1, r, r1);
+#pragma unroll 1
+        for (;;) {
+            int row0, nrows;
+            if (dyn) {
+                if (g0 >= n_dyn) break;
+                row0 = (int)g0 * V2_RC; nrows = V2_RC;
+                g0 = g1; g1 = g2; g2 = atomicAdd(ctr, 1u);
+            } else {
+                if (r >= r1) break;
+                row0 = r; nrows = min(V2_RC, r1 - r); r += V2_RC;
+            }
+            if (!acquire()) break;
+            const int s = (int)(it % V2_SLOTS);
+            sm->meta_row0[s] = row0; sm->meta_nrows[s] = nrows;
+            uint8_t *dst = slots + (size_t)s * V2_SLOT_BYTES;
+            const uint8_t *src = f.W + (size_t)row0 * f.row_stride + f.col_off;
+            mbar_expect_tx(&sm->full[s], (uint32_t)(nrows * f.seg_bytes));
+            if (f.seg_bytes == f.row_stride) bulk_g2s(dst, src, (uint32_t)(nrows * f.seg_bytes), &sm->full[s]);
+            else for (int k = 0; k < nrows; k++) bulk_g2s(dst + (size_t)k * f.seg_bytes, src + (size_t)k * f.row_stride, (uint32_t)f.seg_bytes, &sm->full[s]);
+            it++; n_chunks++;
         }
-        P.run_phase(v2_phase(a.p, 0, 4, 0), ctr + VOX_DEC_LAYERS * 4, a.dynamic);
+        if (dead || !acquire()) break;
+        {   /* end marker: "this CTA has no more rows in this phase" */
+            const int s = (int)(it % V2_SLOTS);
+            sm->meta_row0[s] = 0; sm->meta_nrows[s] = 0;
+            mbar_arrive(&sm->full[s]);
+            it++;
+        }
     }
     if (a.prof) {
         long long *pp = a.prof + (size_t)blockIdx.x * V2_PROF_SLOTS + V2_PROF_SLOTS - 8;
-        pp[0] = P.n_chunks; pp[1] = P.t_wait; pp[2] = P.t_cap; pp[3] = clock64() - t_begin;
+        pp[0] = n_chunks; pp[1] = t_wait; pp[2] = t_cap; pp[3] = clock64() - t_begin;
     }
     /* every bulk copy that was issued must land before the CTA may exit (shared memory is its target) */
-    while (P.landed < P.it) {
+    while (landed < it) {
         long long t0 = 0;
-        const uint32_t j = P.landed;
-        while (!mbar_try_wait(&sm->full[j % V2_SLOTS], (j / V2_SLOTS) & 1u)) spin_guard(t0, P.err, 4);
-        P.landed++;
+        while (!mbar_try_wait(&sm->full[landed % V2_SLOTS], (landed / V2_SLOTS) & 1u)) spin_guard(t0, err, 4);
+        landed++;
     }
 }
 
@@ -323,7 +334,7 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
             if (end) continue;
             const int s = (int)(it % V2_SLOTS);
             const uint32_t par = (it / V2_SLOTS) & 1u;
-            if (!mbar_try_wait(&sm->full[s], par)) {
+            if (!mbar_test_wait(&sm->full[s], par)) {           /* non-blocking probe first: try_wait itself sleeps until the data lands */
                 const long long tw = clock64();
                 long long t0 = 0;
                 while (!mbar_try_wait(&sm->full[s], par)) spin_guard(t0, err, 3);

@@ -142,6 +142,8 @@ typedef struct VbEngine {
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
     VbV2Scratch v2; int v2_checked, v2_ok;
+    const uint8_t *pin_base; size_t pin_bytes;  /* vox_load: the mmap'd checkpoint while it is registered as pinned memory (async H2D) */
+    double load_ms;                             /* wall time of vox_load */
     void *dist;                                 /* VbDist* (vb_dist.c): NCCL communicator of the sequence-sharded encoder */
     float *d_dist_adapter; int dist_adapter_cap;   /* gathered adapter rows of vox_cuda_encode_sharded */
 
@@ -167,6 +169,8 @@ void  vb_device_shutdown(VbEngine *e);
 void *vb_dev_alloc(size_t bytes);
 void *vb_dev_alloc_owned(VbEngine *e, size_t bytes);                    /* freed at shutdown */
 void *vb_dev_upload(VbEngine *e, const void *host, size_t bytes);       /* alloc + H2D + register mirror */
+void  vb_load_copy(VbEngine *e, void *dev, const void *host, size_t bytes);
+void  vb_load_copy_2d(VbEngine *e, void *dev, size_t dpitch, const void *host, size_t spitch, size_t width, size_t height);
 void  vb_register_mirror(VbEngine *e, const void *host, size_t bytes, void *dev);
 void *vb_find_mirror(VbEngine *e, const void *host);
 float *vb_ws(VbEngine *e, int slot, size_t bytes);                      /* workspace, grown on demand */

@@ -12,6 +12,7 @@
 
 #include <math.h>
 #include <string.h>
+#include <sys/time.h>
 
 #define ENC_PFX "mm_streams_embeddings.embedding_module.whisper_encoder"
 #define EMB_PFX "mm_streams_embeddings.embedding_module"
@@ -32,7 +33,7 @@ static uint16_t *get_bf16(safetensors_file_t *sf, const char *who, const char *n
 
 /* ---- device placement helpers ---- */
 static void put(VbEngine *e, void *dev, const void *host, size_t bytes) {
-    VB_CUDA_OK(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
+    vb_load_copy(e, dev, host, bytes);
     vb_register_mirror(e, host, bytes, dev);
 }
 
@@ -48,8 +49,8 @@ static uint16_t *stack3(VbEngine *e, const uint16_t *a, size_t na, const uint16_
 static uint16_t *interleave2(VbEngine *e, const uint16_t *g, const uint16_t *u, int rows, int cols) {
     size_t rb = (size_t)cols * 2;
     uint16_t *d = vb_dev_alloc_owned(e, 2 * (size_t)rows * rb);
-    VB_CUDA_OK(cudaMemcpy2D(d, 2 * rb, g, rb, rb, rows, cudaMemcpyHostToDevice));
-    VB_CUDA_OK(cudaMemcpy2D((uint8_t *)d + rb, 2 * rb, u, rb, rb, rows, cudaMemcpyHostToDevice));
+    vb_load_copy_2d(e, d, 2 * rb, g, rb, rb, rows);                     /* the interleaved layout is built by the copy engine */
+    vb_load_copy_2d(e, (uint8_t *)d + rb, 2 * rb, u, rb, rb, rows);
     return d;
 }
 
@@ -246,7 +247,9 @@ vox_ctx_t *vox_load(const char *model_dir) {
     ctx->use_bf16 = 1;
     ctx->kv_cache_fp16 = 0;
 
-    VB_API_GUARD({ fprintf(stderr, "vox_load: loading failed (device allocation or copy error)\n"); vox_free(ctx); return NULL; });
+    VB_API_GUARD({ fprintf(stderr, "vox_load: loading failed (device allocation or copy error)\n");
+                   if (e->pin_base) { cudaStreamSynchronize(e->stream); cudaHostUnregister((void *)e->pin_base); e->pin_base = NULL; }
+                   vox_free(ctx); return NULL; });
     if (vb_device_init(e) != 0) {
         fprintf(stderr, "vox_load: no usable CUDA device; refusing to load (no CPU fallback)\n");
         free(e);
@@ -266,15 +269,26 @@ vox_ctx_t *vox_load(const char *model_dir) {
     }
     ctx->safetensors = sf;
     if (vox_verbose >= 1) fprintf(stderr, "Loading weights...\n");
+    /* Weight path: the reference "loads" by mmap and pays the page faults in the first matmuls
+     * (voxtral_safetensors.c:225).  Here the mapping is registered read-only as pinned memory, so every tensor goes to HBM with
+     * an asynchronous DMA at PCIe rate straight into its final layout (stacked q|k|v, row-interleaved w1|w3), one sync at the end. */
+    struct timeval tv0; gettimeofday(&tv0, NULL);
+    if (!getenv("VOX_CUDA_NO_HOSTREG")) {
+        if (cudaHostRegister(sf->data, sf->file_size, cudaHostRegisterReadOnly) == cudaSuccess) { e->pin_base = (const uint8_t *)sf->data; e->pin_bytes = sf->file_size; }
+        else cudaGetLastError();
+    }
     if (load_encoder(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load encoder\n"); VB_API_END; vox_free(ctx); return NULL; }
     if (load_adapter(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load adapter\n"); VB_API_END; vox_free(ctx); return NULL; }
     if (load_decoder(e, sf) != 0) { fprintf(stderr, "vox_load: failed to load decoder\n"); VB_API_END; vox_free(ctx); return NULL; }
     update_time_conditioning(e);
     vb_decoder_alloc(e);
+    VB_CUDA_OK(cudaStreamSynchronize(e->stream));
+    if (e->pin_base) { cudaHostUnregister((void *)e->pin_base); e->pin_base = NULL; e->pin_bytes = 0; }
+    { struct timeval tv1; gettimeofday(&tv1, NULL); e->load_ms = (tv1.tv_sec - tv0.tv_sec) * 1e3 + (tv1.tv_usec - tv0.tv_usec) / 1e3; }
     vb_set_default_engine(e);
     if (vox_verbose >= 1)
-        fprintf(stderr, "Model loaded. (%.2f GB of weights resident in HBM on device %d)\n",
-                (double)e->weight_bytes / 1e9, e->device);
+        fprintf(stderr, "Model loaded. (%.2f GB of weights resident in HBM on device %d, %.2f s)\n",
+                (double)e->weight_bytes / 1e9, e->device, e->load_ms / 1e3);
     VB_API_END;
     return ctx;
 }
@@ -340,6 +354,7 @@ void vox_free(vox_ctx_t *ctx) {
 #undef FREE0
     vb_decoder_free(e);
     vox_cuda_dist_shutdown(ctx);
+    if (e->pin_base) { cudaStreamSynchronize(e->stream); cudaHostUnregister((void *)e->pin_base); e->pin_base = NULL; }   /* a failed vox_load */
     vb_device_shutdown(e);
     if (ctx->safetensors) safetensors_close((safetensors_file_t *)ctx->safetensors);
     free(e);

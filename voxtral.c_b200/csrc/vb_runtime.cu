@@ -114,9 +114,27 @@ extern "C" void *vb_dev_alloc_owned(VbEngine *e, size_t bytes) {
     return d;
 }
 
+/* Host -> device copy during vox_load: asynchronous on the engine's stream when the source lies inside the checkpoint mapping
+ * that vox_load registered as pinned memory (DMA straight from the page cache at PCIe rate), synchronous through the driver's
+ * staging buffer otherwise (small malloc'd f32 tensors). */
+extern "C" void vb_load_copy(VbEngine *e, void *dev, const void *host, size_t bytes) {
+    const uint8_t *h = (const uint8_t *)host;
+    if (e->pin_base && h >= e->pin_base && h + bytes <= e->pin_base + e->pin_bytes)
+        VB_CUDA_OK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, e->stream));
+    else
+        VB_CUDA_OK(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
+}
+extern "C" void vb_load_copy_2d(VbEngine *e, void *dev, size_t dpitch, const void *host, size_t spitch, size_t width, size_t height) {
+    const uint8_t *h = (const uint8_t *)host;
+    if (e->pin_base && h >= e->pin_base && h + spitch * height <= e->pin_base + e->pin_bytes)
+        VB_CUDA_OK(cudaMemcpy2DAsync(dev, dpitch, host, spitch, width, height, cudaMemcpyHostToDevice, e->stream));
+    else
+        VB_CUDA_OK(cudaMemcpy2D(dev, dpitch, host, spitch, width, height, cudaMemcpyHostToDevice));
+}
+
 extern "C" void *vb_dev_upload(VbEngine *e, const void *host, size_t bytes) {
     void *d = vb_dev_alloc_owned(e, bytes);
-    VB_CUDA_OK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+    vb_load_copy(e, d, host, bytes);
     vb_register_mirror(e, host, bytes, d);
     return d;
 }

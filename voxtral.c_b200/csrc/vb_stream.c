@@ -847,6 +847,7 @@ int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out) {
     out->last_mel_kernel_ms = e->last_mel_ms;
     out->total_decode_kernel_ms = e->total_decode_ms; out->total_decode_steps = e->total_decode_steps;
     out->total_encoder_ms = e->total_encoder_ms; out->total_encoder_positions = e->total_encoder_positions;
+    out->load_ms = e->load_ms;
     return 0;
 }
 
