@@ -378,6 +378,7 @@ typedef struct {
     double total_encoder_ms;             /* cumulative host-observed time of encoder+adapter passes */
     long long total_encoder_positions;
     double load_ms;                      /* wall time of vox_load (checkpoint -> HBM) */
+    long long verify_passes, verify_tokens;   /* verify mode: weight passes spent / tokens emitted (tokens / passes = tokens per pass) */
 } vox_cuda_info_t;
 int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out);
 const char *vox_cuda_version(void);
@@ -386,6 +387,13 @@ const char *vox_cuda_version(void);
  * 5 = persistent kernel with a decoupled TMA weight stream, dynamic row chunks and up to 8 activation columns
  * (vb_decode_v2.cu).  All produce the same tokens. */
 void vox_cuda_set_decode_mode(vox_ctx_t *ctx, int mode);
+
+/* Exact multi-token decoding of ONE stream: depth 2..8 = that many consecutive positions per weight pass,
+ * the first fed with the last emitted token, the others with drafts (a successor table learned from the stream itself, else
+ * "repeat the last token"); the longest prefix whose drafts were right is accepted, so the ids are those of plain greedy
+ * decoding and a pass yields between 1 and depth tokens.  Pays off when the output is repetitive (streaming pad tokens,
+ * recurring word pieces); costs ~10-30 % per pass otherwise.  Default 1 (off); env VOX_CUDA_VERIFY sets the default. */
+void vox_cuda_set_verify_depth(vox_ctx_t *ctx, int depth);
 
 /* ---- several streams on one GPU sharing one weight pass ----
  * vox_cuda_ctx_fork: a second context on the parent's weights (own decoder KV ring, encoder tail, scratch; shared bf16

@@ -24,10 +24,15 @@ for cfg in configs:
     mode, n = parts[0], int(parts[1]) if len(parts) > 1 and parts[1] else 1
     for k in KEYS:
         os.environ.pop(k, None)
+    verify = 1
     if len(parts) > 2:
         for kv in parts[2].split(","):
             k, v = kv.split("=")
-            os.environ[k] = v
+            if k == "VERIFY":
+                verify = int(v)
+            else:
+                os.environ[k] = v
+    eng.set_verify_depth(verify)
     while len(forks) < n - 1:
         forks.append(eng.fork())
     engines = [eng] + forks[:n - 1]
@@ -57,6 +62,8 @@ for cfg in configs:
         if best is None or dms < best[0]:
             best = (dms, dsteps, ms)
     dms, dsteps, ms = best
+    if verify > 1:
+        print(f"[sweep] verify depth {verify}: {i1['verify_tokens'] - i0['verify_tokens']} tokens in {i1['verify_passes'] - i0['verify_passes']} weight passes")
     print(f"[sweep] {cfg:40s} {seconds:g}s x {n}: decode {dms / max(dsteps, 1):.4f} ms/step ({dsteps} steps), pass {ms:.1f} ms, "
           f"aggregate RTF {n * seconds / (ms / 1e3):.1f}, ids {sorted(set(h(x) for x in ids))}", flush=True)
 for f in forks:

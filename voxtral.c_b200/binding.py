@@ -38,7 +38,8 @@ class CudaInfo(C.Structure):
                 ("last_decode_steps", C.c_int), ("last_encoder_kernel_ms", C.c_double),
                 ("last_encoder_positions", C.c_int), ("last_mel_kernel_ms", C.c_double),
                 ("total_decode_kernel_ms", C.c_double), ("total_decode_steps", C.c_longlong),
-                ("total_encoder_ms", C.c_double), ("total_encoder_positions", C.c_longlong), ("load_ms", C.c_double)]
+                ("total_encoder_ms", C.c_double), ("total_encoder_positions", C.c_longlong), ("load_ms", C.c_double),
+                ("verify_passes", C.c_longlong), ("verify_tokens", C.c_longlong)]
 
 
 def lib():
@@ -110,7 +111,7 @@ def lib():
         "vox_cuda_timer_start": (None, [vp]), "vox_cuda_timer_stop_ms": (C.c_double, [vp]),
         "vox_cuda_stream_token_ids": (i, [vp, c_int_p, i]),
         "vox_cuda_stream_counts": (i, [vp, c_int_p, c_int_p, c_int_p]),
-        "vox_cuda_debug_fail_alloc_after": (None, [C.c_longlong]),
+        "vox_cuda_debug_fail_alloc_after": (None, [C.c_longlong]), "vox_cuda_set_verify_depth": (None, [vp, i]),
         "vox_cuda_ctx_fork": (vp, [vp]), "vox_cuda_stream_set_deferred": (None, [vp, i]),
         "vox_cuda_streams_decode": (i, [C.POINTER(vp), i]),
     }
@@ -203,6 +204,9 @@ class Engine:
 
     def set_decode_mode(self, mode):
         lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "mega": 2, "persist": 3, "tc": 4, "v2": 5}[mode])
+
+    def set_verify_depth(self, depth):
+        lib().vox_cuda_set_verify_depth(self.ctx, int(depth))
 
     def reset_caches(self):
         lib().vox_cuda_reset_caches(self.ctx)

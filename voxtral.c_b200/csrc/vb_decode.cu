@@ -352,6 +352,8 @@ static void set_state(VbEngine *e, int pos, int token, int adapter_row, const fl
 /* returns the decode driver to use: 1 graph, 2 TMA-ring persistent kernel, 3 direct-load persistent kernel, 4 TMA ring + tensor-core consumer */
 static int decode_driver(VbEngine *e) {
     if (e->decode_mode == 0) {
+        const char *vd = getenv("VOX_CUDA_VERIFY");
+        if (vd && e->verify_depth == 0) e->verify_depth = atoi(vd);
         const char *m = getenv("VOX_CUDA_DECODE");
         if (m && !strcmp(m, "graph")) e->decode_mode = 1;
         else if (m && !strcmp(m, "mega")) e->decode_mode = 2;
@@ -387,11 +389,15 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
     while (done < n_steps) {
         int chunk = n_steps - done;
         if (chunk > max_chunk) chunk = max_chunk;
+        int verify_launch = 0;
         if (mega) {
             VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
             if (driver == 5) {
                 VbV2Col col = { e, d_adapter, adapter_row + done, chunk, prev_token, pos + done };
-                if (vb_decoder_v2_launch(e, &col, 1, chunk, 0, NULL) != 0) VB_FAIL("v2 decode launch failed");
+                /* exact multi-token decoding while the drafted positions cannot wrap the KV ring (vb_decode_v2.cu, verify mode) */
+                const int depth = e->verify_depth > 1 && pos + done + chunk + e->verify_depth <= VB_KV_SLOTS ? e->verify_depth : 1;
+                verify_launch = depth > 1;
+                if (vb_decoder_v2_launch(e, &col, depth, chunk, depth > 1, NULL) != 0) VB_FAIL("v2 decode launch failed");
             } else if (driver == 2) vb_decoder_mega_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             else if (driver == 4) vb_decoder_tc_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             else vb_decoder_persist_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
@@ -421,6 +427,7 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
         }
         VB_CUDA_OK(cudaMemcpy(e->h_tokens_pinned, e->d_tokens, (size_t)st.n_out * 4, cudaMemcpyDeviceToHost));
         float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); total_ms += ms;
+        if (verify_launch) { e->verify_passes += st.pad[0]; e->verify_tokens += st.n_out; }
         if (!mega) e->launches += (unsigned long long)st.n_out * STEP_KERNELS;
         memcpy(out_tokens_host + done, e->h_tokens_pinned, (size_t)st.n_out * 4);
         done += st.n_out;

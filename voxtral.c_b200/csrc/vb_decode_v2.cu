@@ -46,6 +46,7 @@
 #define V2_PROF_SLOTS  320
 #define V2_MAX_STEPS   2048
 #define V2_NSPLIT_MAX  20
+#define V2_DRAFT_TAB   512                     /* entries of the per-CTA successor table (verify mode) */
 
 struct V2Col {
     const float *adapter;                      /* adapter rows of this stream */
@@ -78,6 +79,9 @@ struct V2Smem {
     /* column state, identical in every CTA */
     int c_pos[V2_MAXB], c_token[V2_MAXB], c_arow[V2_MAXB], c_done[V2_MAXB], c_nout[V2_MAXB], c_left[V2_MAXB];
     const float *c_adapter[V2_MAXB]; float *c_kv_k[V2_MAXB], *c_kv_v[V2_MAXB], *c_logits[V2_MAXB]; int *c_tokens[V2_MAXB];
+    /* verify mode (one stream, columns = drafted positions): stream state, a small successor table as the drafter, counters */
+    int v_pos, v_token, v_arow, v_left, v_nout, v_eos, v_passes;
+    int dr_key[V2_DRAFT_TAB], dr_succ[V2_DRAFT_TAB];
     volatile int abort_flag, is_last;
 };
 
@@ -584,6 +588,29 @@ __device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float 
     }
 }
 
+/* ------------------------------------------------------------------ verify mode: exact multi-token decoding */
+/* The greedy loop of voxtral.c:1056-1093 emits one token per weight pass.  Here the columns of a pass are CONSECUTIVE positions
+ * of one stream: column 0 gets the last emitted token (always valid), column j a DRAFT of the j-th next token.  Every column's
+ * argmax o_j is exact given its inputs, so o_0 is always the next token, and o_j is the (j+1)-th next token iff drafts 1..j were
+ * right (draft_j == o_{j-1}).  The longest such prefix is accepted: identical ids, between 1 and nb tokens per weight pass.
+ * K/V rows written by rejected columns lie at positions the next pass rewrites before anything reads them (no ring wrap: the
+ * host only uses this mode while pos + nb <= 8192).  Drafter: a 512-entry table of "token -> the token that followed it last
+ * time" kept identically in every CTA's shared memory, falling back to repeating the last token (streaming ASR output is
+ * dominated by repeated [STREAMING_PAD] and by re-occurring word pieces). */
+__device__ __forceinline__ int v2_draft_next(const V2Smem *sm, int tok) {
+    const int h = tok & (V2_DRAFT_TAB - 1);
+    return sm->dr_key[h] == tok ? sm->dr_succ[h] : tok;
+}
+__device__ __forceinline__ void v2_verify_columns(V2Smem *sm, int nb) {
+    int tok = sm->v_token;
+    for (int j = 0; j < V2_MAXB; j++) {
+        const bool on = j < nb && j < sm->v_left && !sm->v_eos;
+        sm->c_pos[j] = sm->v_pos + j; sm->c_arow[j] = on ? sm->v_arow + j : 0; sm->c_token[j] = tok;
+        sm->c_done[j] = on ? 0 : 1;
+        tok = v2_draft_next(sm, tok);
+    }
+}
+
 /* ------------------------------------------------------------------ the kernel */
 extern __shared__ __align__(1024) uint8_t v2_smem_raw[];
 
@@ -608,6 +635,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
             sm->c_done[b] = on ? 0 : 1; sm->c_nout[b] = 0; sm->c_left[b] = on ? a.col[b].n_steps : 0;
             sm->c_adapter[b] = a.col[b].adapter; sm->c_kv_k[b] = a.col[b].kv_k; sm->c_kv_v[b] = a.col[b].kv_v;
             sm->c_logits[b] = a.col[b].logits; sm->c_tokens[b] = a.col[b].tokens;
+        }
+        if (a.verify) {
+            /* one stream: column j processes position pos+j with input token (j == 0: the last emitted token, else draft j);
+             * all columns share the stream's KV ring / adapter rows; columns beyond the remaining adapter rows are off */
+            sm->v_pos = a.col[0].pos0; sm->v_token = a.col[0].token0; sm->v_arow = a.col[0].arow0; sm->v_left = a.col[0].n_steps;
+            sm->v_nout = 0; sm->v_eos = 0; sm->v_passes = 0;
+            for (int i = 0; i < V2_DRAFT_TAB; i++) { sm->dr_key[i] = -1; sm->dr_succ[i] = -1; }
+            v2_verify_columns(sm, a.nb);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -636,7 +671,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
         /* residual stream rows owned by this CTA: x = adapter[arow] + tok_emb[token] (voxtral.c:1057-1061) */
         for (int i = tid; i < (my_r1 - my_r0) * NB; i += V2_CONS) {
             const int b = i % NB, r = my_r0 + i / NB;
-            const float *ar = sm->c_adapter[b] + (size_t)sm->c_arow[b] * VOX_DEC_DIM;
+            const float *ar = sm->c_adapter[b] + (size_t)(sm->c_done[b] ? 0 : sm->c_arow[b]) * VOX_DEC_DIM;   /* finished column: any valid row */
             const uint16_t *er = p.tok_emb + (size_t)sm->c_token[b] * VOX_DEC_DIM;
             a.x[(size_t)b * VOX_DEC_DIM + r] = ar[r] + __uint_as_float((uint32_t)er[r] << 16);
         }
@@ -654,7 +689,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
             int seg_bytes = VOX_DEC_DIM * 2, NT = V2_CONS;
             if (sub == 0 && layer == 0) {
                 x.fill([&](int b, int j) {
-                    const float *ar = sm->c_adapter[b] + (size_t)sm->c_arow[b] * VOX_DEC_DIM + tid * 8;
+                    const float *ar = sm->c_adapter[b] + (size_t)(sm->c_done[b] ? 0 : sm->c_arow[b]) * VOX_DEC_DIM + tid * 8;
                     const uint16_t *er = p.tok_emb + (size_t)sm->c_token[b] * VOX_DEC_DIM + tid * 8;
                     return ar[j] + __uint_as_float((uint32_t)er[j] << 16);
                 });
@@ -741,7 +776,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 for (int b = 0; b < NB; b++) sm->cand[tid >> 5][b] = best[b];
             }
             v2_bar();
-            if (tid == 0) {
+            if (tid == 0 && !a.verify) {
                 for (int b = 0; b < NB; b++) {
                     if (sm->c_done[b]) continue;
                     unsigned long long m = 0ull;
@@ -752,6 +787,26 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                     if (tok == VB_TOKEN_EOS) sm->c_done[b] = 2;
                     else if (sm->c_left[b] <= 0) sm->c_done[b] = 1;
                 }
+            }
+            if (tid == 0 && a.verify) {
+                /* accept the longest prefix whose drafts were right; every CTA takes the same decision */
+                int prev = sm->v_token;
+                sm->v_passes++;
+                for (int b = 0; b < NB; b++) {
+                    if (sm->c_done[b]) break;
+                    if (b > 0 && sm->c_token[b] != prev) break;            /* draft b was wrong: o_b was computed from a wrong input */
+                    unsigned long long m = 0ull;
+                    for (int w = 0; w < V2_CW; w++) if (sm->cand[w][b] > m) m = sm->cand[w][b];
+                    const int tok = cand_index(m);
+                    if (blockIdx.x == 0) sm->c_tokens[0][sm->v_nout] = tok;
+                    const int h = prev & (V2_DRAFT_TAB - 1);
+                    sm->dr_key[h] = prev; sm->dr_succ[h] = tok;             /* learn: prev was followed by tok */
+                    sm->v_nout++; sm->v_pos++; sm->v_arow++; sm->v_left--;
+                    prev = tok;
+                    if (tok == VB_TOKEN_EOS) { sm->v_eos = 1; break; }
+                }
+                sm->v_token = prev;
+                v2_verify_columns(sm, a.nb);
             }
             v2_bar();
         }
@@ -765,6 +820,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 VbDecState st;
                 st.pos = sm->c_pos[b]; st.token = sm->c_token[b]; st.eos = sm->c_done[b] == 2; st.n_out = sm->c_nout[b];
                 st.adapter_row = sm->c_arow[b]; st.pad[0] = st.pad[1] = st.pad[2] = 0;
+                if (a.verify) {
+                    st.pos = sm->v_pos; st.token = sm->v_token; st.eos = sm->v_eos; st.n_out = b == 0 ? sm->v_nout : 0;
+                    st.adapter_row = sm->v_arow; st.pad[0] = sm->v_passes;       /* weight passes spent on n_out tokens */
+                }
                 a.st_out[b] = st;
             }
         }
@@ -818,6 +877,7 @@ static int v2_alloc(VbEngine *e) {
     s->bar = (unsigned int *)vb_dev_alloc_owned(e, 256);
     s->ctr = (unsigned int *)vb_dev_alloc_owned(e, (size_t)V2_MAX_STEPS * V2_SUBPHASES * 4);
     s->st = (VbDecState *)vb_dev_alloc_owned(e, sizeof(VbDecState) * V2_MAXB);
+    s->logits_extra = (float *)vb_dev_alloc_owned(e, (size_t)(V2_MAXB - 1) * VOX_VOCAB_SIZE * 4);
     s->prof = NULL;
     e->weight_bytes = wb;
     return 0;
@@ -857,16 +917,18 @@ extern "C" int vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb,
     V2Args a;
     memset(&a, 0, sizeof a);
     a.p = vb_make_dec_params(lead, 1);
+    VbV2Scratch *s = &lead->v2;
     for (int b = 0; b < nb; b++) {
-        VbEngine *e = cols[b].engine;
+        const VbV2Col *c = verify ? &cols[0] : &cols[b];               /* verify: every column is a position of the one stream */
+        VbEngine *e = c->engine;
         vb_decoder_alloc(e);
-        a.col[b].adapter = cols[b].d_adapter; a.col[b].kv_k = e->d_kv_k; a.col[b].kv_v = e->d_kv_v;
-        a.col[b].logits = e->d_logits; a.col[b].tokens = e->d_tokens;
-        a.col[b].pos0 = cols[b].pos; a.col[b].token0 = cols[b].prev_token; a.col[b].arow0 = cols[b].adapter_row;
-        a.col[b].n_steps = cols[b].n_steps < n_steps ? cols[b].n_steps : n_steps;
+        a.col[b].adapter = c->d_adapter; a.col[b].kv_k = e->d_kv_k; a.col[b].kv_v = e->d_kv_v;
+        a.col[b].logits = (verify && b > 0) ? s->logits_extra + (size_t)(b - 1) * VOX_VOCAB_SIZE : e->d_logits;
+        a.col[b].tokens = e->d_tokens;
+        a.col[b].pos0 = c->pos; a.col[b].token0 = c->prev_token; a.col[b].arow0 = c->adapter_row;
+        a.col[b].n_steps = c->n_steps < n_steps ? c->n_steps : n_steps;
     }
     for (int b = nb; b < V2_MAXB; b++) { a.col[b] = a.col[0]; a.col[b].n_steps = 0; }
-    VbV2Scratch *s = &lead->v2;
     a.x = s->x; a.q = s->q; a.attn_out = s->attn_out; a.gate = s->gate;
     a.part_m = s->part_m; a.part_l = s->part_l; a.part_o = s->part_o; a.argmax = s->argmax;
     a.bar = s->bar; a.ctr = s->ctr; a.st_out = s->st;

@@ -91,7 +91,7 @@ typedef struct {
 
 /* scratch of the batched persistent decode kernel (vb_decode_v2.cu), owned by the engine that launches it */
 typedef struct {
-    float *x, *q, *attn_out, *gate, *part_m, *part_l, *part_o;
+    float *x, *q, *attn_out, *gate, *part_m, *part_l, *part_o, *logits_extra;
     unsigned long long *argmax;
     unsigned int *bar, *ctr;
     VbDecState *st;
@@ -142,6 +142,8 @@ typedef struct VbEngine {
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
     VbV2Scratch v2; int v2_checked, v2_ok;
+    int verify_depth;                           /* > 1: exact multi-token decoding with that many positions per weight pass (vb_decode_v2.cu) */
+    long long verify_passes, verify_tokens;     /* weight passes spent / tokens emitted in verify mode */
     const uint8_t *pin_base; size_t pin_bytes;  /* vox_load: the mmap'd checkpoint while it is registered as pinned memory (async H2D) */
     double load_ms;                             /* wall time of vox_load */
     void *dist;                                 /* VbDist* (vb_dist.c): NCCL communicator of the sequence-sharded encoder */

@@ -848,6 +848,7 @@ int vox_cuda_get_info(vox_ctx_t *ctx, vox_cuda_info_t *out) {
     out->total_decode_kernel_ms = e->total_decode_ms; out->total_decode_steps = e->total_decode_steps;
     out->total_encoder_ms = e->total_encoder_ms; out->total_encoder_positions = e->total_encoder_positions;
     out->load_ms = e->load_ms;
+    out->verify_passes = e->verify_passes; out->verify_tokens = e->verify_tokens;
     return 0;
 }
 
@@ -878,6 +879,11 @@ int vox_cuda_debug_copy_logits(vox_ctx_t *ctx, float *h_logits) {
 
 void vox_cuda_set_decode_mode(vox_ctx_t *ctx, int mode) {
     if (ctx) vb_engine(ctx)->decode_mode = mode;
+}
+
+void vox_cuda_set_verify_depth(vox_ctx_t *ctx, int depth) {
+    if (!ctx) return;
+    vb_engine(ctx)->verify_depth = depth < 2 ? 1 : depth > 8 ? 8 : depth;
 }
 
 void vox_cuda_reset_caches(vox_ctx_t *ctx) {
