@@ -62,7 +62,7 @@ struct V2Args {
     float *x, *q, *attn_out, *gate;            /* [nb][3072], [nb][4096], [nb][4096], [nb][9216] */
     float *part_m, *part_l, *part_o;           /* [nb][20][32], [nb][20][32], [nb][20][32][128] */
     unsigned long long *argmax;                /* [grid][V2_MAXB] */
-    unsigned int *bar;                         /* [0] grid barrier, [16..23] attention tickets, [32] error word */
+    unsigned int *bar;                         /* [0] grid barrier, [32] error word, [64 + column * 8 + kv head] attention tickets */
     unsigned int *ctr;                         /* [n_steps][V2_SUBPHASES] chunk counters of the dynamic phases */
     VbDecState *st_out;                        /* [nb] */
     int nb, n_steps, inflight_max, dynamic, verify, dbg;
@@ -180,24 +180,9 @@ __device__ void v2_producer(V2Smem *sm, uint8_t *slots, const V2Args &a) {
         const V2Phase f = v2_phase(a.p, layer == VOX_DEC_LAYERS ? 0 : layer, ph, part);
         const bool dyn = f.dyn && a.dynamic;
         unsigned int *ctr = a.ctr + (size_t)step * V2_SUBPHASES + (ph == 4 ? VOX_DEC_LAYERS * 4 : layer * 4 + ph);
-        /* chunk source: dynamic = ids from the phase's global counter, three grabs ahead; static = this CTA's row range */
-        unsigned int g0 = 0, g1 = 0, g2 = 0;
-        int r = 0, r1 = 0;
-        const unsigned int n_dyn = (unsigned int)(f.total_rows / V2_RC);
-        if (dyn) { g0 = atomicAdd(ctr, 1u); g1 = atomicAdd(ctr, 1u); g2 = atomicAdd(ctr, 1u); }
-        else v2_static_rows(f.total_rows, f.dyn ? V2_RC : 1, r, r1);
-#pragma unroll 1
-        for (;;) {
-            int row0, nrows;
-            if (dyn) {
-                if (g0 >= n_dyn) break;
-                row0 = (int)g0 * V2_RC; nrows = V2_RC;
-                g0 = g1; g1 = g2; g2 = atomicAdd(ctr, 1u);
-            } else {
-                if (r >= r1) break;
-                row0 = r; nrows = min(V2_RC, r1 - r); r += V2_RC;
-            }
-            if (!acquire()) break;
+        /* one chunk: slot, meta, expect_tx, bulk copy (one copy when the rows are contiguous, else one per row segment) */
+        auto emit = [&](int row0, int nrows) -> bool {
+            if (!acquire()) return false;
             const int s = (int)(it % V2_SLOTS);
             sm->meta_row0[s] = row0; sm->meta_nrows[s] = nrows;
             uint8_t *dst = slots + (size_t)s * V2_SLOT_BYTES;
@@ -206,6 +191,30 @@ __device__ void v2_producer(V2Smem *sm, uint8_t *slots, const V2Args &a) {
             if (f.seg_bytes == f.row_stride) bulk_g2s(dst, src, (uint32_t)(nrows * f.seg_bytes), &sm->full[s]);
             else for (int k = 0; k < nrows; k++) bulk_g2s(dst + (size_t)k * f.seg_bytes, src + (size_t)k * f.row_stride, (uint32_t)f.seg_bytes, &sm->full[s]);
             it++; n_chunks++;
+            return true;
+        };
+        if (dyn) {
+            /* chunk ids from the phase's global counter.  An atomic takes ~2000 cycles when the memory system is busy, twice a
+             * chunk's time: four grabs are kept in flight in four distinct registers (a rotating "g0 = g1" window would read the
+             * newest result every iteration and serialise on it -- measured: 900 cycles per chunk). */
+            const unsigned int n_dyn = (unsigned int)(f.total_rows / V2_RC);
+            unsigned int g[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) g[u] = atomicAdd(ctr, 1u);
+            bool more = true;
+            while (more) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned int id = g[u];
+                    if (id >= n_dyn) { more = false; break; }             /* ids only grow: the other three are past the end too */
+                    g[u] = atomicAdd(ctr, 1u);
+                    if (!emit((int)id * V2_RC, V2_RC)) { more = false; break; }
+                }
+            }
+        } else {
+            int r, r1;
+            v2_static_rows(f.total_rows, f.dyn ? V2_RC : 1, r, r1);
+            for (; r < r1; r += V2_RC) if (!emit(r, min(V2_RC, r1 - r))) break;
         }
         if (dead || !acquire()) break;
         {   /* end marker: "this CTA has no more rows in this phase" */
@@ -320,7 +329,7 @@ __device__ __forceinline__ void v2_dot8(const uint4 w, const V2X<NB> &x, float (
  * epi(row, b, value, lane, valid) runs in the last consumer warp; lane = (chunk * 4 + row_in_chunk) * NB + b. */
 template <int NB, typename Epi>
 __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uint32_t &it, int seg_bytes, int NT,
-                                           const V2X<NB> &x, int &redbuf, int *err, long long &t_stall, int dbg, Epi epi) {
+                                           const V2X<NB> &x, int &redbuf, int *err, long long (&tacc)[5], bool timing, int dbg, Epi epi) {
     constexpr int CPR = NB == 1 ? 4 : NB == 2 ? 2 : 1;     /* chunks per reduction */
     constexpr int HALVES = NB == 8 ? 2 : 1;                /* NB = 8: a chunk's 32 values are reduced as two halves (registers) */
     constexpr int RH = V2_RC / HALVES;                     /* rows per half */
@@ -338,12 +347,14 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
             if (end) continue;
             const int s = (int)(it % V2_SLOTS);
             const uint32_t par = (it / V2_SLOTS) & 1u;
-            if (!mbar_test_wait(&sm->full[s], par)) {           /* non-blocking probe first: try_wait itself sleeps until the data lands */
-                const long long tw = clock64();
+            long long tq0 = 0;
+            if (timing) tq0 = clock64();
+            {
                 long long t0 = 0;
                 while (!mbar_try_wait(&sm->full[s], par)) spin_guard(t0, err, 3);
-                t_stall += clock64() - tw;
             }
+            long long tq1 = 0;
+            if (timing) { tq1 = clock64(); tacc[0] += tq1 - tq0; }
             const int nrows = sm->meta_nrows[s];
             row0s[c] = sm->meta_row0[s]; nrs[c] = nrows;
             if (nrows == 0) end = true;
@@ -378,14 +389,21 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm->empty[s]);     /* the rows are in registers: the slot can be refilled */
             it++;
+            if (timing) tacc[1] += clock64() - tq1;
         }
         if (got == 0) break;
         if (dbg & 2) continue;
+        long long tr0 = 0;
+        if (timing) tr0 = clock64();
         if (HALVES == 1) {
             const float tot = v2_transpose_reduce<16>(acc, lane);
             if (!(lane & 1)) sm->red[redbuf][warp][lane >> 1] = tot;
         }
+        long long tr1 = 0;
+        if (timing) { tr1 = clock64(); tacc[2] += tr1 - tr0; }
         v2_bar();
+        long long tr2 = 0;
+        if (timing) { tr2 = clock64(); tacc[3] += tr2 - tr1; }
         if (warp == V2_CW - 1) {
             constexpr int NV = 16 * HALVES;                 /* values in this reduction: lane < NV */
             float sum = 0.f;
@@ -398,6 +416,7 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
 #pragma unroll
             for (int k = 1; k < CPR; k++) if (c == k) { row0 = row0s[k]; nr = nrs[k]; }
             epi(row0 + r, lane % NB, sum, lane, lane < NV && r < nr);
+            if (timing) tacc[4] += clock64() - tr2;
         }
         redbuf ^= 1;
     }
@@ -462,18 +481,30 @@ __device__ __forceinline__ void v2_rmsnorm(V2X<NB> &x, const float *__restrict__
 }
 
 /* ------------------------------------------------------------------ attention */
-/* kv head h is served by the CTAs with (cta & 7) == h; they split the valid ring slots of each column between them.  Inside a
- * CTA the 12 warps take interleaved slots (the 4 query heads of the kv head share each K/V row read), merge through shared
- * memory to one partial per query head and column, publish it; the last CTA to arrive for a kv head (atomic ticket) combines. */
+/* Work unit = (column, kv head): the CTAs are dealt round-robin to the 8 * n_active pairs and those of a pair split the valid
+ * ring slots of that column between them (one column: 18-19 CTAs per kv head; eight columns: 2-3 CTAs per pair), so a CTA
+ * handles exactly one pair per layer whatever NB is.  Inside the CTA the 12 warps take interleaved slots (the 4 query heads of
+ * the kv head share each K/V row read), merge through shared memory to one partial per query head, publish it; the last CTA
+ * to arrive for the pair (atomic ticket) combines the pair's partials into attn_out.  voxtral_kernels.c:412-482. */
 template <int NB>
 __device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float *att_scr, int layer) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kvh = blockIdx.x & 7, si = blockIdx.x >> 3;
-    const int nsplit = (gridDim.x >> 3) + ((int)(gridDim.x & 7) > kvh ? 1 : 0);
+    int nact = 0, my_b = -1;
+    {
+        int idx[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) if (!sm->c_done[b]) idx[nact++] = b;
+        if (nact == 0) return;
+        const int pair_of_cta = (int)(blockIdx.x % (unsigned)(8 * nact));
+#pragma unroll
+        for (int k = 0; k < NB; k++) if (k < nact && k == pair_of_cta / 8) my_b = idx[k];
+    }
+    const int npairs = 8 * nact;
+    const int pair = (int)(blockIdx.x % (unsigned)npairs), si = (int)(blockIdx.x / (unsigned)npairs);
+    const int nsplit = (int)(gridDim.x / (unsigned)npairs) + ((int)(gridDim.x % (unsigned)npairs) > pair ? 1 : 0);
+    const int kvh = pair & 7, b = my_b;
     const float scale = 1.0f / sqrtf((float)HD);
-#pragma unroll 1
-    for (int b = 0; b < NB; b++) {
-        if (sm->c_done[b]) continue;
+    {
         const int pos = sm->c_pos[b];
         const int n_valid = min(pos + 1, VB_KV_SLOTS);
         const int s0 = (int)((long long)n_valid * si / nsplit), s1 = (int)((long long)n_valid * (si + 1) / nsplit);
@@ -548,43 +579,41 @@ __device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float 
         }
         v2_bar();
     }
-    /* ticket: the last CTA of this kv head combines all columns */
+    /* ticket: the last CTA of this (column, kv head) combines */
+    unsigned int *ticket = a.bar + 64 + b * 8 + kvh;
     if (tid == 0) {
         __threadfence();
-        unsigned int old = atomicAdd(&a.bar[16 + kvh], 1u);
+        unsigned int old = atomicAdd(ticket, 1u);
         int last = (old == (unsigned int)(nsplit - 1));
-        if (last) { a.bar[16 + kvh] = 0u; __threadfence(); }
+        if (last) { *ticket = 0u; __threadfence(); }
         sm->is_last = last;
     }
     v2_bar();
-    if (sm->is_last) {
-        for (int pi2 = warp; pi2 < 4 * NB; pi2 += V2_CW) {
-            const int b = pi2 >> 2, h = kvh * 4 + (pi2 & 3);
-            if (sm->c_done[b]) continue;
-            float mi = -1e30f, li = 0.f;
-            if (lane < nsplit) {
-                mi = __ldcg(a.part_m + ((size_t)b * V2_NSPLIT_MAX + lane) * VOX_DEC_HEADS + h);
-                li = __ldcg(a.part_l + ((size_t)b * V2_NSPLIT_MAX + lane) * VOX_DEC_HEADS + h);
-            }
-            float M = mi;
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o2));
-            float wi = li > 0.f ? expf(mi - M) : 0.f;
-            float L = vb_warp_sum(wi * li);
-            float4 O = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 ov[V2_NSPLIT_MAX];
-#pragma unroll
-            for (int i = 0; i < V2_NSPLIT_MAX; i++)
-                ov[i] = i < nsplit ? __ldcg(reinterpret_cast<const float4 *>(a.part_o + (((size_t)b * V2_NSPLIT_MAX + i) * VOX_DEC_HEADS + h) * HD + lane * 4))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < V2_NSPLIT_MAX; i++) {
-                float c = __shfl_sync(0xffffffffu, wi, i);
-                O.x = fmaf(c, ov[i].x, O.x); O.y = fmaf(c, ov[i].y, O.y); O.z = fmaf(c, ov[i].z, O.z); O.w = fmaf(c, ov[i].w, O.w);
-            }
-            float inv = L > 0.f ? 1.0f / L : 0.f;
-            *reinterpret_cast<float4 *>(a.attn_out + (size_t)b * VB_DEC_Q + h * HD + lane * 4) = make_float4(O.x * inv, O.y * inv, O.z * inv, O.w * inv);
+    if (sm->is_last && warp < 4) {
+        const int h = kvh * 4 + warp;
+        float mi = -1e30f, li = 0.f;
+        if (lane < nsplit) {
+            mi = __ldcg(a.part_m + ((size_t)b * V2_NSPLIT_MAX + lane) * VOX_DEC_HEADS + h);
+            li = __ldcg(a.part_l + ((size_t)b * V2_NSPLIT_MAX + lane) * VOX_DEC_HEADS + h);
         }
+        float M = mi;
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o2));
+        float wi = li > 0.f ? expf(mi - M) : 0.f;
+        float L = vb_warp_sum(wi * li);
+        float4 O = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ov[V2_NSPLIT_MAX];
+#pragma unroll
+        for (int i = 0; i < V2_NSPLIT_MAX; i++)
+            ov[i] = i < nsplit ? __ldcg(reinterpret_cast<const float4 *>(a.part_o + (((size_t)b * V2_NSPLIT_MAX + i) * VOX_DEC_HEADS + h) * HD + lane * 4))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < V2_NSPLIT_MAX; i++) {
+            float c = __shfl_sync(0xffffffffu, wi, i);
+            O.x = fmaf(c, ov[i].x, O.x); O.y = fmaf(c, ov[i].y, O.y); O.z = fmaf(c, ov[i].z, O.z); O.w = fmaf(c, ov[i].w, O.w);
+        }
+        float inv = L > 0.f ? 1.0f / L : 0.f;
+        *reinterpret_cast<float4 *>(a.attn_out + (size_t)b * VB_DEC_Q + h * HD + lane * 4) = make_float4(O.x * inv, O.y * inv, O.z * inv, O.w * inv);
     }
 }
 
@@ -657,7 +686,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
     uint32_t it = 0;
     unsigned int gen = 0;
     int redbuf = 0, prof_n = 0;
-    long long t_stall = 0;                                     /* cycles this thread waited for weight chunks (whole launch) */
+    long long tacc[5] = { 0, 0, 0, 0, 0 };                    /* profiled launches: cycles of this thread in wait-for-data / math / reduce / CTA barrier / epilogue */
+    const bool timing = a.prof != nullptr && (lane == 0);
     int my_r0, my_r1;                                          /* residual-stream rows this CTA owns (static wo / w2 partition) */
     v2_static_rows(VOX_DEC_DIM, 1, my_r0, my_r1);
 
@@ -704,7 +734,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 v2_rmsnorm<NB>(x, nw, sub == 3 ? p.ada + (size_t)layer * VOX_DEC_DIM : nullptr, sm);
             }
             const float *inv_freq = p.inv_freq;
-            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, err, t_stall, a.dbg, [&](int row, int b, float v, int, bool valid) {
+            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, err, tacc, timing, a.dbg, [&](int row, int b, float v, int, bool valid) {
                 const float other = __shfl_xor_sync(0xffffffffu, v, NB);    /* row ^ 1 of the same column: RoPE pair / (gate, up) pair */
                 if (!valid) return;
                 switch (sub) {
@@ -812,8 +842,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
         }
         V2PROF();
     }
+    if (a.prof && lane == 0 && (tid == 0 || tid == V2_CONS - 32)) {            /* warp 0 and the epilogue warp */
+        long long *pp = a.prof + (size_t)blockIdx.x * V2_PROF_SLOTS + V2_PROF_SLOTS - (tid == 0 ? 20 : 14);
+        for (int i = 0; i < 5; i++) pp[i] = tacc[i];
+    }
     if (tid == 0) {
-        if (a.prof) a.prof[(size_t)blockIdx.x * V2_PROF_SLOTS + V2_PROF_SLOTS - 1] = t_stall;
         sm->abort_flag = 1;                                            /* the producer may be ahead of an early exit (EOS) */
         if (blockIdx.x == 0) {
             for (int b = 0; b < a.nb; b++) {
@@ -874,7 +907,7 @@ static int v2_alloc(VbEngine *e) {
     s->part_l = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * V2_NSPLIT_MAX * VOX_DEC_HEADS * 4);
     s->part_o = (float *)vb_dev_alloc_owned(e, (size_t)V2_MAXB * V2_NSPLIT_MAX * VOX_DEC_HEADS * HD * 4);
     s->argmax = (unsigned long long *)vb_dev_alloc_owned(e, (size_t)e->sm_count * V2_MAXB * 8);
-    s->bar = (unsigned int *)vb_dev_alloc_owned(e, 256);
+    s->bar = (unsigned int *)vb_dev_alloc_owned(e, 1024);    /* [0] grid barrier, [32] error word, [64..127] attention tickets */
     s->ctr = (unsigned int *)vb_dev_alloc_owned(e, (size_t)V2_MAX_STEPS * V2_SUBPHASES * 4);
     s->st = (VbDecState *)vb_dev_alloc_owned(e, sizeof(VbDecState) * V2_MAXB);
     s->logits_extra = (float *)vb_dev_alloc_owned(e, (size_t)(V2_MAXB - 1) * VOX_VOCAB_SIZE * 4);
@@ -901,9 +934,12 @@ static void v2_prof_report(VbEngine *e, const V2Args &a) {
         fprintf(stderr, " | layer=%.0f | logits=%lld bar=%lld feedback=%lld step=%lld\n", tot / (VOX_DEC_LAYERS - 2),
                 t[26 * 10 + 1] - t[26 * 10], t[26 * 10 + 2] - t[26 * 10 + 1], t[26 * 10 + 3] - t[26 * 10 + 2], t[26 * 10 + 3] - t[0]);
         const long long *q = t + V2_PROF_SLOTS - 8;
-        fprintf(stderr, "[v2 prof nb=%d] cta %3d whole launch: producer %lld chunks in %lld cycles (%.0f/chunk; waiting for a free slot %.0f, for the in-flight cap %.0f per chunk); "
-                        "consumer thread 0 waited %.0f cycles per chunk for data\n", a.nb, ctas[ci], q[0], q[3], (double)q[3] / (double)(q[0] ? q[0] : 1),
-                (double)q[1] / (double)(q[0] ? q[0] : 1), (double)q[2] / (double)(q[0] ? q[0] : 1), (double)t[V2_PROF_SLOTS - 1] / (double)(q[0] ? q[0] : 1));
+        const double nc = (double)(q[0] ? q[0] : 1);
+        fprintf(stderr, "[v2 prof nb=%d] cta %3d whole launch: producer %lld chunks in %lld cycles (%.0f/chunk; waiting for a free slot %.0f, for the in-flight cap %.0f per chunk)\n",
+                a.nb, ctas[ci], q[0], q[3], (double)q[3] / nc, (double)q[1] / nc, (double)q[2] / nc);
+        const long long *w0 = t + V2_PROF_SLOTS - 20, *w11 = t + V2_PROF_SLOTS - 14;
+        fprintf(stderr, "[v2 prof nb=%d] cta %3d consumer cycles per chunk  warp 0: wait-data %.0f math %.0f reduce %.0f cta-barrier %.0f | epilogue warp: wait-data %.0f math %.0f reduce %.0f cta-barrier %.0f epilogue %.0f\n",
+                a.nb, ctas[ci], w0[0] / nc, w0[1] / nc, w0[2] / nc, w0[3] / nc, w11[0] / nc, w11[1] / nc, w11[2] / nc, w11[3] / nc, w11[4] / nc);
     }
     free(h);
 }
@@ -945,7 +981,7 @@ extern "C" int vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb,
         if (cudaMemsetAsync(s->prof, 0, (size_t)lead->sm_count * V2_PROF_SLOTS * 8, lead->stream) != cudaSuccess) return -1;
         a.prof = s->prof; a.prof_step = atoi(ev);
     }
-    if (cudaMemsetAsync(s->bar, 0, 256, lead->stream) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(s->bar, 0, 1024, lead->stream) != cudaSuccess) return -1;
     if (cudaMemsetAsync(s->ctr, 0, (size_t)n_steps * V2_SUBPHASES * 4, lead->stream) != cudaSuccess) return -1;
     void *args[] = { &a };
     const void *fn = nb == 1 ? (const void *)k_dec_v2<1> : nb == 2 ? (const void *)k_dec_v2<2> : nb <= 4 ? (const void *)k_dec_v2<4> : (const void *)k_dec_v2<8>;
