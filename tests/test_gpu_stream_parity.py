@@ -63,12 +63,12 @@ def test_decode_drivers_agree(engine):
     pcm = read_wav_f32(synth_wav(2))
     g = golden("synth_s2_oneshot")
     out = {}
-    for mode in ("graph", "mega", "persist", "tc", "v2"):
+    for mode in ("graph", "persist", "v2"):
         engine.set_decode_mode(mode)
         out[mode], text, _ = run_stream(engine, pcm)
         check_against(g, out[mode], text)
     engine.set_decode_mode("auto")
-    assert out["graph"].tolist() == out["mega"].tolist() == out["persist"].tolist() == out["tc"].tolist() == out["v2"].tolist()
+    assert out["graph"].tolist() == out["persist"].tolist() == out["v2"].tolist()
 
 
 def test_chunked_1s_tokens_match_reference(engine):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Same recording through several decode drivers: token ids must agree; prints device ms per decode step for each.
-   python tools/compare_drivers.py [seconds] [mode ...]      (modes: graph mega persist tc)"""
+   python tools/compare_drivers.py [seconds] [mode ...]      (modes: graph persist v2)"""
 import os
 import sys
 
@@ -13,7 +13,7 @@ from conftest import ensure_synth_model, read_wav_f32, synth_wav  # noqa: E402
 import vbload  # noqa: E402
 
 seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 30.0
-modes = sys.argv[2:] or ["persist", "tc"]
+modes = sys.argv[2:] or ["persist", "v2"]
 vb = vbload.load()
 eng = vb.Engine(ensure_synth_model())
 pcm = read_wav_f32(synth_wav(seconds))

@@ -203,7 +203,7 @@ class Engine:
         lib().vox_set_delay(self.ctx, int(delay_ms))
 
     def set_decode_mode(self, mode):
-        lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "mega": 2, "persist": 3, "tc": 4, "v2": 5}[mode])
+        lib().vox_cuda_set_decode_mode(self.ctx, {"auto": 0, "graph": 1, "persist": 3, "v2": 5}[mode])
 
     def set_verify_depth(self, depth):
         lib().vox_cuda_set_verify_depth(self.ctx, int(depth))

@@ -349,27 +349,20 @@ static void set_state(VbEngine *e, int pos, int token, int adapter_row, const fl
     VB_CUDA_OK(cudaStreamSynchronize(e->stream));   /* h is on the stack */
 }
 
-/* returns the decode driver to use: 1 graph, 2 TMA-ring persistent kernel, 3 direct-load persistent kernel, 4 TMA ring + tensor-core consumer */
+/* returns the decode driver to use: 1 CUDA graph of per-phase kernels, 3 direct-load persistent kernel, 5 v2 persistent kernel */
 static int decode_driver(VbEngine *e) {
     if (e->decode_mode == 0) {
         const char *vd = getenv("VOX_CUDA_VERIFY");
         if (vd && e->verify_depth == 0) e->verify_depth = atoi(vd);
         const char *m = getenv("VOX_CUDA_DECODE");
         if (m && !strcmp(m, "graph")) e->decode_mode = 1;
-        else if (m && !strcmp(m, "mega")) e->decode_mode = 2;
         else if (m && !strcmp(m, "persist")) e->decode_mode = 3;
-        else if (m && !strcmp(m, "tc")) e->decode_mode = 4;
         else if (m && !strcmp(m, "v2")) e->decode_mode = 5;
         else e->decode_mode = vb_decoder_v2_supported(e) ? 5 : vb_decoder_persist_supported(e) ? 3 : 1;
     }
-    if (e->decode_mode == 2 && !vb_decoder_mega_supported(e)) {   /* also sets the kernel's shared-memory attribute */
-        fprintf(stderr, "voxtral_b200: TMA-ring megakernel requested but unavailable on this device\n"); abort();
-    }
+    if (e->decode_mode != 1 && e->decode_mode != 3 && e->decode_mode != 5) e->decode_mode = vb_decoder_v2_supported(e) ? 5 : vb_decoder_persist_supported(e) ? 3 : 1;
     if (e->decode_mode == 3 && !vb_decoder_persist_supported(e)) {
         fprintf(stderr, "voxtral_b200: persistent decode kernel requested but cooperative launch is unavailable\n"); abort();
-    }
-    if (e->decode_mode == 4 && !vb_decoder_tc_supported(e)) {
-        fprintf(stderr, "voxtral_b200: tensor-core ring decode kernel requested but unavailable on this device\n"); abort();
     }
     if (e->decode_mode == 5 && !vb_decoder_v2_supported(e)) {
         fprintf(stderr, "voxtral_b200: v2 decode kernel requested but unavailable on this device\n"); abort();
@@ -398,9 +391,7 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
                 const int depth = e->verify_depth > 1 && pos + done + chunk + e->verify_depth <= VB_KV_SLOTS ? e->verify_depth : 1;
                 verify_launch = depth > 1;
                 if (vb_decoder_v2_launch(e, &col, depth, chunk, depth > 1, NULL) != 0) VB_FAIL("v2 decode launch failed");
-            } else if (driver == 2) vb_decoder_mega_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
-            else if (driver == 4) vb_decoder_tc_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
-            else vb_decoder_persist_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
+            } else vb_decoder_persist_launch(e, d_adapter, adapter_row + done, chunk, prev_token, pos + done);
             VB_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
         } else {
             set_state(e, pos + done, prev_token, adapter_row + done, d_adapter);
@@ -422,7 +413,7 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
         VB_CUDA_OK(cudaMemcpyAsync(&st, driver == 5 ? e->v2.st : e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream));
         cudaError_t serr = cudaStreamSynchronize(e->stream);
         if (serr != cudaSuccess) {
-            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), driver == 1 ? "graph" : driver == 2 ? "tma-ring" : driver == 4 ? "tc-ring" : driver == 5 ? "v2" : "persist");
+            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), driver == 1 ? "graph" : driver == 5 ? "v2" : "persist");
             vb_cuda_fail(serr, __FILE__, __LINE__);
         }
         VB_CUDA_OK(cudaMemcpy(e->h_tokens_pinned, e->d_tokens, (size_t)st.n_out * 4, cudaMemcpyDeviceToHost));

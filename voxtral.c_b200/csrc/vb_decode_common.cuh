@@ -1,7 +1,8 @@
 /*
- * vb_decode_common.cuh -- pieces shared by the two decode drivers:
- *   vb_decode.cu       one kernel per phase, replayed as a CUDA graph (validation / fallback path)
- *   vb_decode_mega.cu  one persistent cooperative kernel per batch of steps (the fast path)
+ * vb_decode_common.cuh -- pieces shared by the decode drivers:
+ *   vb_decode.cu          one kernel per phase, replayed as a CUDA graph (validation / fallback path)
+ *   vb_decode_persist.cu  round 1's persistent cooperative kernel (direct streaming loads)
+ *   vb_decode_v2.cu       the persistent kernel with a decoupled TMA weight stream and up to 8 activation columns (default)
  */
 #ifndef VB_DECODE_COMMON_CUH
 #define VB_DECODE_COMMON_CUH

@@ -1,21 +1,19 @@
 /*
- * vb_decode_persist.cu -- persistent cooperative decode kernel, direct-streaming variant.
+ * vb_decode_persist.cu -- persistent cooperative decode kernel, direct-streaming variant (round 1's default; now the
+ * A/B reference for vb_decode_v2.cu and the fallback when that kernel does not fit a device).
  *
- * Same structure as vb_decode_mega.cu (one CTA per SM runs the whole multi-step greedy loop; phases are
- * separated by grid barriers; the token feedback stays on the device) but the weights are NOT staged through
- * shared memory: every thread streams its own k-columns with 128-bit ld.global.nc.L1::no_allocate loads,
- * 16 rows in flight per thread (the GEMV core that reaches 99% of the measured HBM peak inside the logits
- * phase, profiles/r01_launches_graph.md).  What a phase boundary costs -- barrier latency, skew between
- * CTAs, the activation reload -- is hidden differently: just before a CTA enters a grid barrier it issues ONE
- * cp.async.bulk.prefetch.L2 for the next `l2_ahead` bytes of its own slab schedule.  HBM therefore keeps
- * streaming while the SMs wait, and the first rows of the next phase are L2 hits.
+ * One CTA per SM runs the whole multi-step greedy loop; the 131 phases of a step are separated by grid barriers; the token
+ * feedback stays on the device.  Weights are NOT staged through shared memory: every thread streams its own k-columns with
+ * 128-bit ld.global.nc.L1::no_allocate loads, 16 rows in flight per thread (the GEMV core reaches 99% of the measured HBM
+ * peak inside the logits phase).  What a phase boundary costs -- drain, barrier, activation reload, RMSNorm, ramp, ~5.5 us --
+ * is NOT hidden here; the step sits at 0.59 of the HBM roofline (profiles/r01_decode.md, which also records the L2-prefetch,
+ * TMA-ring and mma.sync variants that were tried: they live on under tools/experiments/).
  *
  * Reference semantics: voxtral_decoder.c:586-706 per step, voxtral.c:1056-1093 for the loop.
  */
 #include "vb_decode_persist_common.cuh"
 #include <string.h>
 
-#define PK_L2_AHEAD 0   /* measured: L2 prefetch only moves time from the phases into the barriers (profiles/r01_decode_persist.md) */
 
 /* y[row] = W[row,:] . x for the CTA's rows, 16 rows of 128-bit loads in flight per thread. */
 template <int CPT, typename Epi>
@@ -62,48 +60,6 @@ __device__ __forceinline__ void gemv_stream(const Phase &f, int K, int NT, const
     }
 }
 
-/* Walks the CTA's slab schedule (step -> layer -> qkv, wo, w13, w2 -> logits) in bytes. */
-struct PrefetchCursor {
-    int step, layer, ph;
-    long long off;            /* bytes of the cursor's slab already prefetched */
-    long long pf_total;       /* schedule bytes prefetched so far */
-    long long cons_total;     /* schedule bytes whose phase has been consumed */
-    __device__ void start() { step = 0; layer = 0; ph = 0; off = 0; pf_total = 0; cons_total = 0; }
-    __device__ void advance_phase() {
-        off = 0;
-        if (ph == 4) { ph = 0; layer = 0; step++; }
-        else if (ph == 3) { if (layer == VOX_DEC_LAYERS - 1) ph = 4; else { layer++; ph = 0; } }
-        else ph++;
-    }
-    /* called by ONE thread when the phase (cl, cp) of step cs has just been consumed */
-    __device__ void consumed(const DecParams &p, int cs, int cl, int cp) {
-        Phase done = phase_of(p, cl, cp);
-        cons_total += (long long)done.nrows * done.row_bytes;
-        if (pf_total < cons_total) {                    /* cursor fell behind consumption: jump to the next phase */
-            step = cs; layer = cl; ph = cp; advance_phase();
-            pf_total = cons_total;
-        }
-    }
-    /* prefetch schedule bytes into L2 until `ahead` bytes beyond the consumption point are covered */
-    __device__ void extend(const DecParams &p, int n_steps, int ahead) {
-        while (step < n_steps && pf_total < cons_total + ahead) {
-            Phase f = phase_of(p, layer, ph);
-            const long long slab = (long long)f.nrows * f.row_bytes;
-            long long want = cons_total + ahead - pf_total;
-            long long piece = slab - off < want ? slab - off : want;
-            piece &= ~15ll;
-            if (piece <= 0) break;
-            l2_prefetch(reinterpret_cast<const uint8_t *>(f.W) + (size_t)f.row0 * f.row_bytes + off, (uint32_t)piece);
-            off += piece; pf_total += piece;
-            if (off >= slab) advance_phase();
-        }
-    }
-    __device__ void after_phase(const DecParams &p, int n_steps, int cs, int cl, int cp, int ahead) {
-        consumed(p, cs, cl, cp);
-        extend(p, n_steps, ahead);
-    }
-};
-
 __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
     __shared__ float red[2][16][MK_GROUP];
     __shared__ float sred[16];
@@ -118,8 +74,6 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
     int pos = a.pos0, token = a.token0, arow = a.adapter_row0;
     const float *adapter = *p.adapter_pp;
     int n_done = 0, eos = 0, prof_n = 0;
-    PrefetchCursor pc;
-    pc.start();
 
     for (int step = 0; step < a.n_steps; step++) {
         const float *arow_p = adapter + (size_t)arow * VOX_DEC_DIM;
@@ -166,12 +120,10 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                 });
             }
             PROF(1);
-            if (tid == 0) pc.after_phase(p, a.n_steps, step, layer, 0, a.l2_ahead);
             grid_barrier(a.bar, gen, a.err);
             PROF(2);
             mega_attention(p, layer, pos, &is_last, att_scr, a.bar + 16);
             PROF(3);
-            if (tid == 0) pc.extend(p, a.n_steps, 2 * a.l2_ahead);      /* the attention phase streamed no weights */
             grid_barrier(a.bar, gen, a.err);
             PROF(4);
             {   /* ---- wo + residual ---- */
@@ -185,7 +137,6 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                 });
             }
             PROF(5);
-            if (tid == 0) pc.after_phase(p, a.n_steps, step, layer, 1, a.l2_ahead);
             grid_barrier(a.bar, gen, a.err);
             PROF(6);
             {   /* ---- RMSNorm*(1+ada) -> [w1|w3] -> SiLU(g)*u ---- */
@@ -201,7 +152,6 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                 });
             }
             PROF(7);
-            if (tid == 0) pc.after_phase(p, a.n_steps, step, layer, 2, a.l2_ahead);
             grid_barrier(a.bar, gen, a.err);
             PROF(8);
             {   /* ---- w2 + residual ---- */
@@ -215,7 +165,6 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
                 });
             }
             PROF(9);
-            if (tid == 0) pc.after_phase(p, a.n_steps, step, layer, 3, a.l2_ahead);
             grid_barrier(a.bar, gen, a.err);
         }
         PROF(10);
@@ -243,7 +192,6 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
             }
         }
         PROF(11);
-        if (tid == 0) pc.after_phase(p, a.n_steps, step, 0, 4, a.l2_ahead);
         grid_barrier(a.bar, gen, a.err);
         PROF(12);
         {   /* global argmax: every CTA reduces the per-CTA candidates, so every CTA knows the token */
@@ -303,12 +251,45 @@ extern "C" int vb_decoder_persist_launch(VbEngine *e, const float *d_adapter, in
     a.p = vb_make_dec_params(e, 1);
     a.n_steps = n_steps; a.pos0 = pos; a.token0 = prev_token; a.adapter_row0 = adapter_row;
     a.bar = e->d_mega_bar; a.err = (int *)(e->d_mega_bar + 32);
-    const char *la = getenv("VOX_CUDA_L2_AHEAD");
-    a.l2_ahead = la ? atoi(la) : PK_L2_AHEAD;
+    a.l2_ahead = 0;
     vb_mega_prof_begin(e, a, n_steps);
     void *args[] = { &a };
     VB_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_dec_persist, dim3(e->sm_count), dim3(MK_CONS), args, 0, e->stream));
     e->launches += 1;
     vb_mega_prof_report(e, a, "persist");
     return 0;
+}
+
+/* ---- optional in-kernel phase profile (VOX_CUDA_MEGA_PROF=<step>) shared by both persistent kernels ---- */
+static long long *g_d_prof = NULL;
+void vb_mega_prof_begin(VbEngine *e, MegaArgs &a, int n_steps) {
+    a.prof = NULL; a.prof_step = -1;
+    const char *pe = getenv("VOX_CUDA_MEGA_PROF");
+    if (pe && n_steps > atoi(pe)) {
+        if (!g_d_prof) g_d_prof = (long long *)vb_dev_alloc((size_t)e->sm_count * MK_PROF_SLOTS * 8);
+        VB_CUDA_OK(cudaMemsetAsync(g_d_prof, 0, (size_t)e->sm_count * MK_PROF_SLOTS * 8, e->stream));
+        a.prof = g_d_prof; a.prof_step = atoi(pe);
+    }
+}
+void vb_mega_prof_report(VbEngine *e, const MegaArgs &a, const char *label) {
+    if (!a.prof) return;
+    size_t n = (size_t)e->sm_count * MK_PROF_SLOTS;
+    long long *h = (long long *)malloc(n * 8);
+    VB_CUDA_OK(cudaMemcpyAsync(h, g_d_prof, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    VB_CUDA_OK(cudaStreamSynchronize(e->stream));
+    /* per-layer stamps: 0 start, 1 qkv done, 2 bar, 3 attention done, 4 bar, 5 wo, 6 bar, 7 w13, 8 bar, 9 w2, (next 0 after bar) */
+    static const char *names[10] = { "qkv", "bar", "attn", "bar", "wo", "bar", "w13", "bar", "w2", "bar" };
+    const int ctas[3] = { 0, e->sm_count / 2, e->sm_count - 1 };
+    for (int ci = 0; ci < 3; ci++) {
+        long long *t = h + (size_t)ctas[ci] * MK_PROF_SLOTS;
+        double sum[10] = { 0 };
+        for (int l = 1; l < VOX_DEC_LAYERS - 1; l++)
+            for (int k = 0; k < 10; k++) sum[k] += (double)(t[l * 10 + k + 1] - t[l * 10 + k]);
+        fprintf(stderr, "[%s prof] cta %3d cycles/layer:", label, ctas[ci]);
+        double tot = 0;
+        for (int k = 0; k < 10; k++) { fprintf(stderr, " %s=%.0f", names[k], sum[k] / (VOX_DEC_LAYERS - 2)); tot += sum[k]; }
+        fprintf(stderr, " | layer=%.0f | logits=%lld bar=%lld step=%lld\n", tot / (VOX_DEC_LAYERS - 2),
+                t[26 * 10 + 1] - t[26 * 10], t[26 * 10 + 2] - t[26 * 10 + 1], t[26 * 10 + 2] - t[0]);
+    }
+    free(h);
 }

@@ -1,8 +1,8 @@
 /*
  * vb_decode_persist_common.cuh -- building blocks shared by the persistent decode kernels
- * (vb_decode_persist.cu: direct streaming loads, the default; vb_decode_mega.cu: TMA weight ring + CUDA-core consumer;
- * vb_decode_tc.cu: TMA ring over a decode-tiled weight image + mma.sync consumer).
- * All run 512 compute threads per CTA that synchronise on named barrier 1.
+ * (vb_decode_v2.cu: TMA weight ring, dynamic row chunks, up to 8 activation columns -- the default;
+ * vb_decode_persist.cu: direct streaming loads, 512 compute threads synchronising on named barrier 1):
+ * PTX wrappers (mbarrier, cp.async.bulk, release/acquire), the grid barrier, the static slab schedule.
  */
 #ifndef VB_DECODE_PERSIST_COMMON_CUH
 #define VB_DECODE_PERSIST_COMMON_CUH

@@ -326,10 +326,12 @@ __device__ __forceinline__ void v2_dot8(const uint4 w, const V2X<NB> &x, float (
  * Partial sums of 16 (row, column) pairs are reduced together -- 4 chunks x 4 rows for one column, 2 chunks for two columns,
  * one chunk for four, half a chunk for eight -- so the cost of a reduction (15 shuffles, one shared-memory pass, one named
  * barrier) is the same per 16 outputs whatever NB is, and a slot is released as soon as its rows are in the accumulators.
- * epi(row, b, value, lane, valid) runs in the last consumer warp; lane = (chunk * 4 + row_in_chunk) * NB + b. */
+ * epi(row, b, value, lane, valid) runs in ONE warp per reduction, the warps taking turns (grp % 12): the epilogue is a latency
+ * chain (12 shared-memory reads, the sum, sincosf / expf, global stores) that would otherwise put the same warp on the critical
+ * path of every reduction (measured: 284 of 876 cycles per chunk).  lane = (chunk * 4 + row_in_chunk) * NB + b. */
 template <int NB, typename Epi>
 __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uint32_t &it, int seg_bytes, int NT,
-                                           const V2X<NB> &x, int &redbuf, int *err, long long (&tacc)[5], bool timing, int dbg, Epi epi) {
+                                           const V2X<NB> &x, int &redbuf, uint32_t &grp, int *err, long long (&tacc)[5], bool timing, int dbg, Epi epi) {
     constexpr int CPR = NB == 1 ? 4 : NB == 2 ? 2 : 1;     /* chunks per reduction */
     constexpr int HALVES = NB == 8 ? 2 : 1;                /* NB = 8: a chunk's 32 values are reduced as two halves (registers) */
     constexpr int RH = V2_RC / HALVES;                     /* rows per half */
@@ -404,7 +406,7 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
         v2_bar();
         long long tr2 = 0;
         if (timing) { tr2 = clock64(); tacc[3] += tr2 - tr1; }
-        if (warp == V2_CW - 1) {
+        if (warp == (int)(grp % V2_CW)) {
             constexpr int NV = 16 * HALVES;                 /* values in this reduction: lane < NV */
             float sum = 0.f;
             if (lane < NV) {
@@ -418,6 +420,7 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
             epi(row0 + r, lane % NB, sum, lane, lane < NV && r < nr);
             if (timing) tacc[4] += clock64() - tr2;
         }
+        grp++;
         redbuf ^= 1;
     }
 }
@@ -686,6 +689,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
     uint32_t it = 0;
     unsigned int gen = 0;
     int redbuf = 0, prof_n = 0;
+    uint32_t grp = 0;                                          /* reductions so far: the epilogue warp of a reduction is grp % 12 */
     long long tacc[5] = { 0, 0, 0, 0, 0 };                    /* profiled launches: cycles of this thread in wait-for-data / math / reduce / CTA barrier / epilogue */
     const bool timing = a.prof != nullptr && (lane == 0);
     int my_r0, my_r1;                                          /* residual-stream rows this CTA owns (static wo / w2 partition) */
@@ -734,7 +738,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 v2_rmsnorm<NB>(x, nw, sub == 3 ? p.ada + (size_t)layer * VOX_DEC_DIM : nullptr, sm);
             }
             const float *inv_freq = p.inv_freq;
-            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, err, tacc, timing, a.dbg, [&](int row, int b, float v, int, bool valid) {
+            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, grp, err, tacc, timing, a.dbg, [&](int row, int b, float v, int, bool valid) {
                 const float other = __shfl_xor_sync(0xffffffffu, v, NB);    /* row ^ 1 of the same column: RoPE pair / (gate, up) pair */
                 if (!valid) return;
                 switch (sub) {
@@ -778,13 +782,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 if (sub != 6) V2PROF();
             }
         }
-        if (tid >= V2_CONS - 32) {                                     /* per-CTA argmax per column */
+        {   /* per-CTA argmax per column: every warp ran some of the logits epilogues (its lanes' column is lane % NB) */
 #pragma unroll
             for (int o = 16; o >= NB; o >>= 1) {
                 unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
                 if (other > best) best = other;
             }
-            if (lane < NB) a.argmax[(size_t)blockIdx.x * V2_MAXB + lane] = best;
+            v2_bar();
+            if (lane < NB) sm->cand[tid >> 5][lane] = best;
+            v2_bar();
+            if (tid < NB) {
+                unsigned long long m = 0ull;
+#pragma unroll
+                for (int w = 0; w < V2_CW; w++) if (sm->cand[w][tid] > m) m = sm->cand[w][tid];
+                a.argmax[(size_t)blockIdx.x * V2_MAXB + tid] = m;
+            }
         }
         V2PROF();
         v2_grid_barrier(a.bar, gen, err);

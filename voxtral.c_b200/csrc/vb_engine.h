@@ -136,9 +136,8 @@ typedef struct VbEngine {
     int *d_tokens;  int tokens_cap;
     int *h_tokens_pinned;
     float *d_embed_in;                          /* [3072] staging for the host-pointer API */
-    uint16_t *d_tc_img;                         /* decode-tiled copy of the decoder matrices for the tensor-core ring kernel (vb_decode_tc.cu) */
     unsigned int *d_mega_bar;                   /* grid-barrier counter + error word of the persistent kernel */
-    int decode_mode;                            /* 0 = auto, 1 = CUDA-graph phases, 2 = persistent kernel with TMA weight ring, 3 = persistent kernel, direct loads, 4 = persistent kernel, TMA ring + mma.sync consumer */
+    int decode_mode;                            /* 0 = auto, 1 = CUDA-graph phases, 3 = persistent kernel with direct loads (round 1), 5 = v2 persistent kernel */
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
     VbV2Scratch v2; int v2_checked, v2_ok;
@@ -190,14 +189,8 @@ int  vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int adapter_row, 
 int  vb_decoder_step_from_embed(VbEngine *e, const float *d_embed, int pos, float *logits_host);
 void vb_decoder_prefill_dev(VbEngine *e, const float *d_embeds, int n, int start_pos);
 
-/* vb_decode_mega.cu */
-int  vb_decoder_mega_supported(VbEngine *e);
-int  vb_decoder_mega_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
-
 /* vb_decode_persist.cu */
 void vb_alt_candidates(VbEngine *e, int best, int text_min, float *z, float ev[3], int idx[3]);
-int  vb_decoder_tc_supported(VbEngine *e);
-int  vb_decoder_tc_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 int  vb_decoder_persist_supported(VbEngine *e);
 int  vb_decoder_persist_launch(VbEngine *e, const float *d_adapter, int adapter_row, int n_steps, int prev_token, int pos);
 

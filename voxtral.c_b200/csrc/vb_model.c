@@ -309,7 +309,7 @@ vox_ctx_t *vox_cuda_ctx_fork(vox_ctx_t *parent) {
     e->d_x = e->d_q = e->d_attn_out = e->d_gate = e->d_logits = NULL;
     e->d_part_m = e->d_part_l = e->d_part_o = NULL; e->d_argmax = NULL;
     e->d_tokens = NULL; e->tokens_cap = 0; e->h_tokens_pinned = NULL; e->d_embed_in = NULL;
-    e->d_tc_img = NULL; e->d_mega_bar = NULL; e->step_graph_ready = 0;
+    e->d_mega_bar = NULL; e->step_graph_ready = 0;
     memset(&e->v2, 0, sizeof e->v2);
     memset(e->ws, 0, sizeof e->ws); memset(e->ws_bytes, 0, sizeof e->ws_bytes);
     e->d_enc_tail_k = e->d_enc_tail_v = NULL; e->enc_tail_len = 0;
