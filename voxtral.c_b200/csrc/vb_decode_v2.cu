@@ -66,7 +66,7 @@ struct V2Args {
     unsigned int *ctr;                         /* [n_steps][V2_SUBPHASES] chunk counters of the dynamic phases */
     unsigned int *flags;                       /* [0..2] rows of w1|w3 done per third (monotonic), [8 + column * 8 + kv head] attention sequence number */
     VbDecState *st_out;                        /* [nb] */
-    int nb, n_steps, inflight_max, dynamic, verify, dbg;
+    int nb, n_steps, inflight_max, dynamic, verify, dbg, w13_flags, att_flags;
     long long *prof; int prof_step;
 };
 
@@ -338,7 +338,8 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
     constexpr int RH = V2_RC / HALVES;                     /* rows per half */
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const bool active = t < NT;
-    bool end = false;
+    bool end = false, ready = false;
+    unsigned int pend[3] = { 0u, 0u, 0u };                  /* rows of w1|w3 whose outputs this warp wrote but has not published yet */
     while (!end) {
         float acc[16];
 #pragma unroll
@@ -352,7 +353,7 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
             const uint32_t par = (it / V2_SLOTS) & 1u;
             long long tq0 = 0;
             if (timing) tq0 = clock64();
-            {
+            if (!ready) {                                   /* not already seen complete by the probe of the previous chunk */
                 long long t0 = 0;
                 while (!mbar_try_wait(&sm->full[s], par)) spin_guard(t0, err, 3);
             }
@@ -360,10 +361,12 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
             if (timing) { tq1 = clock64(); tacc[0] += tq1 - tq0; }
             const int nrows = sm->meta_nrows[s];
             row0s[c] = sm->meta_row0[s]; nrs[c] = nrows;
-            if (nrows == 0) end = true;
+            if (nrows == 0) { end = true; ready = false; }
             else {
                 got++;
                 const uint8_t *base = slots + (size_t)s * V2_SLOT_BYTES + (size_t)t * 16;
+                /* probe the NEXT slot now (non-blocking): its ~100-cycle mbarrier round trip overlaps this chunk's math */
+                ready = mbar_test_wait(&sm->full[(it + 1) % V2_SLOTS], ((it + 1) / V2_SLOTS) & 1u);
 #pragma unroll
                 for (int h = 0; h < HALVES; h++) {
                     if (active && !(dbg & 1)) {
@@ -418,19 +421,33 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
             int row0 = row0s[0], nr = nrs[0];
 #pragma unroll
             for (int k = 1; k < CPR; k++) if (c == k) { row0 = row0s[k]; nr = nrs[k]; }
-            epi(row0 + r, lane % NB, sum, lane, lane < NV && r < nr);
-            if (pub) {                                      /* w1|w3: tell the w2 column blocks which thirds of `gate` are complete */
+            if (pub) {
+                /* w1|w3: tell the w2 column blocks which thirds of `gate` are complete.  Publishing needs a GPU-scope release, which
+                 * waits for this warp's outstanding stores (thousands of cycles right after an epilogue's stores -- measured: it doubled
+                 * the phase).  So a warp publishes the rows of its PREVIOUS epilogue, 12 reductions ago, whose stores are long done,
+                 * before it issues new ones; the leftovers are flushed at the end of the phase. */
                 __syncwarp();
                 if (lane == 0) {
-                    __threadfence();
 #pragma unroll
-                    for (int k = 0; k < CPR; k++) if (nrs[k] > 0) red_release_add(pub + row0s[k] / (2 * VOX_DEC_DIM), (unsigned int)nrs[k]);
+                    for (int k = 0; k < 3; k++) if (pend[k]) { red_release_add(pub + k, pend[k]); pend[k] = 0; }
                 }
+            }
+            epi(row0 + r, lane % NB, sum, lane, lane < NV && r < nr);
+            if (pub && lane == 0) {
+#pragma unroll
+                for (int k = 0; k < CPR; k++) if (nrs[k] > 0) pend[row0s[k] / (2 * VOX_DEC_DIM)] += (unsigned int)nrs[k];
             }
             if (timing) tacc[4] += clock64() - tr2;
         }
         grp++;
         redbuf ^= 1;
+    }
+    if (pub) {                                              /* end of the phase: every warp flushes what it still owes */
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) if (pend[k]) red_release_add(pub + k, pend[k]);
+        }
     }
 }
 
@@ -523,9 +540,14 @@ __device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float 
         float4 qv[4];
 #pragma unroll
         for (int hq = 0; hq < 4; hq++) qv[hq] = __ldcg(reinterpret_cast<const float4 *>(a.q + (size_t)b * VB_DEC_Q + (kvh * 4 + hq) * HD + lane * 4));
-        float m[4], l[4]; float4 o[4];
+        /* Online softmax in blocks of 4 slots: the 16 (slot, head) partial dots of a block are reduced over the lanes together
+         * (one transposed reduction: lane L ends up with the score of slot (L >> 3), head ((L >> 1) & 3)), every lane keeps the
+         * running max / sum of ITS head only, and the 16 weights are broadcast back for the 4 x 4-dim accumulators each lane
+         * owns: 40 shuffles and 2 expf per block instead of 80 shuffles and 32 expf with a per-slot update. */
+        float m_my = -1e30f, l_my = 0.f; float4 o[4];
 #pragma unroll
-        for (int hq = 0; hq < 4; hq++) { m[hq] = -1e30f; l[hq] = 0.f; o[hq] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        for (int hq = 0; hq < 4; hq++) o[hq] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int my_u = lane >> 3;
         const float *kb = sm->c_kv_k[b] + (size_t)layer * VB_KV_SLOTS * VB_DEC_KV + kvh * HD + lane * 4;
         const float *vb = sm->c_kv_v[b] + (size_t)layer * VB_KV_SLOTS * VB_DEC_KV + kvh * HD + lane * 4;
         for (int sb = s0 + warp; sb < s1; sb += 4 * V2_CW) {       /* this warp's slots: sb, sb+12, sb+24, sb+36 */
@@ -536,35 +558,41 @@ __device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float 
                 k4[u] = __ldcg(reinterpret_cast<const float4 *>(kb + (size_t)s * VB_DEC_KV));
                 v4[u] = __ldcg(reinterpret_cast<const float4 *>(vb + (size_t)s * VB_DEC_KV));
             }
+            float sc[16];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (sb + V2_CW * u < s1) {
-                    float sc[4];
+            for (int u = 0; u < 4; u++)
 #pragma unroll
-                    for (int hq = 0; hq < 4; hq++)
-                        sc[hq] = qv[hq].x * k4[u].x + qv[hq].y * k4[u].y + qv[hq].z * k4[u].z + qv[hq].w * k4[u].w;
+                for (int hq = 0; hq < 4; hq++)
+                    sc[u * 4 + hq] = qv[hq].x * k4[u].x + qv[hq].y * k4[u].y + qv[hq].z * k4[u].z + qv[hq].w * k4[u].w;
+            const float tot = v2_transpose_reduce<16>(sc, lane);
+            const bool valid = sb + V2_CW * my_u < s1;
+            const float sv = valid ? tot * scale : -1e30f;
+            float bm = fmaxf(sv, __shfl_xor_sync(0xffffffffu, sv, 8));
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+            const float mn = fmaxf(m_my, bm);
+            const float c = expf(m_my - mn);
+            const float pw = valid ? expf(sv - mn) : 0.f;
+            float ps = pw + __shfl_xor_sync(0xffffffffu, pw, 8);
+            ps += __shfl_xor_sync(0xffffffffu, ps, 16);
+            l_my = l_my * c + ps;
+            m_my = mn;
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1)
+            for (int hq = 0; hq < 4; hq++) {
+                const float ch = __shfl_sync(0xffffffffu, c, hq * 2);
+                o[hq].x *= ch; o[hq].y *= ch; o[hq].z *= ch; o[hq].w *= ch;
 #pragma unroll
-                        for (int hq = 0; hq < 4; hq++) sc[hq] += __shfl_xor_sync(0xffffffffu, sc[hq], off);
-#pragma unroll
-                    for (int hq = 0; hq < 4; hq++) {
-                        float sv = sc[hq] * scale;
-                        float mn = fmaxf(m[hq], sv);
-                        float c = expf(m[hq] - mn), pw = expf(sv - mn);
-                        l[hq] = l[hq] * c + pw;
-                        o[hq].x = o[hq].x * c + pw * v4[u].x; o[hq].y = o[hq].y * c + pw * v4[u].y;
-                        o[hq].z = o[hq].z * c + pw * v4[u].z; o[hq].w = o[hq].w * c + pw * v4[u].w;
-                        m[hq] = mn;
-                    }
+                for (int u = 0; u < 4; u++) {
+                    const float pu = __shfl_sync(0xffffffffu, pw, (u * 4 + hq) * 2);
+                    o[hq].x = fmaf(pu, v4[u].x, o[hq].x); o[hq].y = fmaf(pu, v4[u].y, o[hq].y);
+                    o[hq].z = fmaf(pu, v4[u].z, o[hq].z); o[hq].w = fmaf(pu, v4[u].w, o[hq].w);
                 }
             }
         }
-        /* merge the 12 warps: scratch[warp][hq] = {m, l, -, -, o[128]} */
+        /* merge the 12 warps: scratch[warp][hq] = {m, l, -, -, o[128]}; lane 2 hq holds head hq's m and l */
 #pragma unroll
         for (int hq = 0; hq < 4; hq++) {
             float *dst = att_scr + (size_t)(warp * 4 + hq) * 132;
-            if (lane == 0) { dst[0] = m[hq]; dst[1] = l[hq]; }
+            if (lane == hq * 2) { dst[0] = m_my; dst[1] = l_my; }
             *reinterpret_cast<float4 *>(dst + 4 + lane * 4) = o[hq];
         }
         v2_bar();
@@ -742,13 +770,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
              *  - w2 column block j reads gate[3072 j, 3072 (j+1)) = the outputs of rows [6144 j, 6144 (j+1)) of w1|w3: it waits until
              *    that third's row counter says all 6144 rows are done -- normally long true, since this CTA only gets here after
              *    every chunk of w1|w3 has been handed out. */
-            if (sub == 1 || sub == 2) {
+            if ((sub == 1 || sub == 2) && a.att_flags) {
                 if (tid < NB * 4) {
                     const int b = tid >> 2, k = (sub - 1) * 4 + (tid & 3);
                     if (!sm->c_done[b]) { long long t0 = 0; while (ld_acquire_u32(a.flags + 8 + b * 8 + k) < seq) spin_guard(t0, err, 6); }
                 }
                 v2_bar();
-            } else if (sub >= 4 && sub <= 6) {
+            } else if (sub >= 4 && sub <= 6 && a.w13_flags) {
                 if (tid == 0) { long long t0 = 0; while (ld_acquire_u32(a.flags + (sub - 4)) < seq * (unsigned int)(2 * VOX_DEC_DIM)) spin_guard(t0, err, 7); }
                 v2_bar();
             }
@@ -772,7 +800,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 v2_rmsnorm<NB>(x, nw, sub == 3 ? p.ada + (size_t)layer * VOX_DEC_DIM : nullptr, sm);
             }
             const float *inv_freq = p.inv_freq;
-            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, grp, sub == 3 ? a.flags : nullptr, err, tacc, timing, a.dbg, [&](int row, int b, float v, int, bool valid) {
+            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, grp, (sub == 3 && a.w13_flags) ? a.flags : nullptr, err, tacc, timing, a.dbg, [&](int row, int b, float v, int, bool valid) {
                 const float other = __shfl_xor_sync(0xffffffffu, v, NB);    /* row ^ 1 of the same column: RoPE pair / (gate, up) pair */
                 if (!valid) return;
                 switch (sub) {
@@ -808,14 +836,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 V2PROF();
                 v2_attention<NB>(a, sm, att_scr, layer, seq);
                 V2PROF();
-                V2PROF();                                   /* (no barrier: wo waits for the attention flags) */
+                if (!a.att_flags) v2_grid_barrier(a.bar, gen, err);   /* else: wo waits for the attention flags */
+                V2PROF();
             } else if (sub == 2 || sub == 6) {
                 V2PROF();
                 v2_grid_barrier(a.bar, gen, err);
                 if (sub != 6) V2PROF();
             } else if (sub == 3) {
                 V2PROF();
-                V2PROF();                                   /* (no barrier: w2 waits for the w1|w3 row counters) */
+                if (!a.w13_flags) v2_grid_barrier(a.bar, gen, err);   /* else: w2 waits for the w1|w3 row counters */
+                V2PROF();
             }
         }
         {   /* per-CTA argmax per column: every warp ran some of the logits epilogues (its lanes' column is lane % NB) */
@@ -1023,6 +1053,8 @@ extern "C" int vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb,
     if (a.inflight_max < 1) a.inflight_max = 1;
     if (a.inflight_max > V2_SLOTS) a.inflight_max = V2_SLOTS;
     a.dynamic = (ev = getenv("VOX_CUDA_V2_DYNAMIC")) ? atoi(ev) : 1;
+    a.att_flags = (ev = getenv("VOX_CUDA_V2_ATTFLAGS")) ? atoi(ev) : 0;   /* 1: wo column blocks wait for per-(column, kv head) flags instead of a grid barrier after attention */
+    a.w13_flags = (ev = getenv("VOX_CUDA_V2_W13FLAGS")) ? atoi(ev) : 0;   /* 1: w2 column blocks wait for row counters instead of a grid barrier after w1|w3 */
     a.dbg = (ev = getenv("VOX_CUDA_V2_DBG")) ? atoi(ev) : 0;     /* diagnostics only (results are wrong): 1 = no FMAs, 2 = no reductions/epilogues */
     a.prof = NULL; a.prof_step = -1;
     if ((ev = getenv("VOX_CUDA_V2_PROF")) && n_steps > atoi(ev)) {
