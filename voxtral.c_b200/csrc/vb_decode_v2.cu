@@ -64,9 +64,8 @@ struct V2Args {
     unsigned long long *argmax;                /* [grid][V2_MAXB] */
     unsigned int *bar;                         /* [0] grid barrier, [32] error word, [64 + column * 8 + kv head] attention tickets */
     unsigned int *ctr;                         /* [n_steps][V2_SUBPHASES] chunk counters of the dynamic phases */
-    unsigned int *flags;                       /* [0..2] rows of w1|w3 done per third (monotonic), [8 + column * 8 + kv head] attention sequence number */
     VbDecState *st_out;                        /* [nb] */
-    int nb, n_steps, inflight_max, dynamic, verify, dbg, w13_flags, att_flags;
+    int nb, n_steps, inflight_max, dynamic, verify, dbg;
     long long *prof; int prof_step;
 };
 
@@ -332,14 +331,13 @@ __device__ __forceinline__ void v2_dot8(const uint4 w, const V2X<NB> &x, float (
  * path of every reduction (measured: 284 of 876 cycles per chunk).  lane = (chunk * 4 + row_in_chunk) * NB + b. */
 template <int NB, typename Epi>
 __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uint32_t &it, int seg_bytes, int NT,
-                                           const V2X<NB> &x, int &redbuf, uint32_t &grp, unsigned int *pub, int *err, long long (&tacc)[5], bool timing, int dbg, Epi epi) {
+                                           const V2X<NB> &x, int &redbuf, uint32_t &grp, int *err, long long (&tacc)[5], bool timing, int dbg, Epi epi) {
     constexpr int CPR = NB == 1 ? 4 : NB == 2 ? 2 : 1;     /* chunks per reduction */
     constexpr int HALVES = NB == 8 ? 2 : 1;                /* NB = 8: a chunk's 32 values are reduced as two halves (registers) */
     constexpr int RH = V2_RC / HALVES;                     /* rows per half */
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const bool active = t < NT;
     bool end = false, ready = false;
-    unsigned int pend[3] = { 0u, 0u, 0u };                  /* rows of w1|w3 whose outputs this warp wrote but has not published yet */
     while (!end) {
         float acc[16];
 #pragma unroll
@@ -421,33 +419,11 @@ __device__ __forceinline__ void v2_consume(V2Smem *sm, const uint8_t *slots, uin
             int row0 = row0s[0], nr = nrs[0];
 #pragma unroll
             for (int k = 1; k < CPR; k++) if (c == k) { row0 = row0s[k]; nr = nrs[k]; }
-            if (pub) {
-                /* w1|w3: tell the w2 column blocks which thirds of `gate` are complete.  Publishing needs a GPU-scope release, which
-                 * waits for this warp's outstanding stores (thousands of cycles right after an epilogue's stores -- measured: it doubled
-                 * the phase).  So a warp publishes the rows of its PREVIOUS epilogue, 12 reductions ago, whose stores are long done,
-                 * before it issues new ones; the leftovers are flushed at the end of the phase. */
-                __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < 3; k++) if (pend[k]) { red_release_add(pub + k, pend[k]); pend[k] = 0; }
-                }
-            }
             epi(row0 + r, lane % NB, sum, lane, lane < NV && r < nr);
-            if (pub && lane == 0) {
-#pragma unroll
-                for (int k = 0; k < CPR; k++) if (nrs[k] > 0) pend[row0s[k] / (2 * VOX_DEC_DIM)] += (unsigned int)nrs[k];
-            }
             if (timing) tacc[4] += clock64() - tr2;
         }
         grp++;
         redbuf ^= 1;
-    }
-    if (pub) {                                              /* end of the phase: every warp flushes what it still owes */
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) if (pend[k]) red_release_add(pub + k, pend[k]);
-        }
     }
 }
 
@@ -516,7 +492,7 @@ __device__ __forceinline__ void v2_rmsnorm(V2X<NB> &x, const float *__restrict__
  * the kv head share each K/V row read), merge through shared memory to one partial per query head, publish it; the last CTA
  * to arrive for the pair (atomic ticket) combines the pair's partials into attn_out.  voxtral_kernels.c:412-482. */
 template <int NB>
-__device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float *att_scr, int layer, uint32_t seq) {
+__device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float *att_scr, int layer) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int nact = 0, my_b = -1;
     {
@@ -655,13 +631,6 @@ __device__ __forceinline__ void v2_attention(const V2Args &a, V2Smem *sm, float 
         float inv = L > 0.f ? 1.0f / L : 0.f;
         *reinterpret_cast<float4 *>(a.attn_out + (size_t)b * VB_DEC_Q + h * HD + lane * 4) = make_float4(O.x * inv, O.y * inv, O.z * inv, O.w * inv);
     }
-    if (sm->is_last) {                                     /* publish: attn_out of this (column, kv head) is complete for layer `seq` */
-        v2_bar();
-        if (tid == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.flags + 8 + b * 8 + kvh), "r"(seq) : "memory");
-        }
-    }
 }
 
 /* ------------------------------------------------------------------ verify mode: exact multi-token decoding */
@@ -734,7 +703,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
     unsigned int gen = 0;
     int redbuf = 0, prof_n = 0;
     uint32_t grp = 0;                                          /* reductions so far: the epilogue warp of a reduction is grp % 12 */
-    uint32_t seq = 0;                                          /* layers started so far: sequence number of the dependency flags */
     long long tacc[5] = { 0, 0, 0, 0, 0 };                    /* profiled launches: cycles of this thread in wait-for-data / math / reduce / CTA barrier / epilogue */
     const bool timing = a.prof != nullptr && (lane == 0);
     int my_r0, my_r1;                                          /* residual-stream rows this CTA owns (static wo / w2 partition) */
@@ -763,23 +731,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
             const int layer = idx / 7;
             const int sub = layer == VOX_DEC_LAYERS ? 7 : idx - layer * 7;
             if (sub == 0 || sub == 7) V2PROF();
-            if (sub == 0) seq++;
-            /* Two of the five dependencies of a layer need no grid barrier:
-             *  - wo column block p reads attn_out of kv heads 4p..4p+3: it waits for the sequence numbers that the combining CTA of
-             *    each (column, kv head) publishes after writing attn_out;
-             *  - w2 column block j reads gate[3072 j, 3072 (j+1)) = the outputs of rows [6144 j, 6144 (j+1)) of w1|w3: it waits until
-             *    that third's row counter says all 6144 rows are done -- normally long true, since this CTA only gets here after
-             *    every chunk of w1|w3 has been handed out. */
-            if ((sub == 1 || sub == 2) && a.att_flags) {
-                if (tid < NB * 4) {
-                    const int b = tid >> 2, k = (sub - 1) * 4 + (tid & 3);
-                    if (!sm->c_done[b]) { long long t0 = 0; while (ld_acquire_u32(a.flags + 8 + b * 8 + k) < seq) spin_guard(t0, err, 6); }
-                }
-                v2_bar();
-            } else if (sub >= 4 && sub <= 6 && a.w13_flags) {
-                if (tid == 0) { long long t0 = 0; while (ld_acquire_u32(a.flags + (sub - 4)) < seq * (unsigned int)(2 * VOX_DEC_DIM)) spin_guard(t0, err, 7); }
-                v2_bar();
-            }
             /* ---- this phase's activation columns: 8 values x NB per thread ---- */
             V2X<NB> x;
             int seg_bytes = VOX_DEC_DIM * 2, NT = V2_CONS;
@@ -800,7 +751,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 v2_rmsnorm<NB>(x, nw, sub == 3 ? p.ada + (size_t)layer * VOX_DEC_DIM : nullptr, sm);
             }
             const float *inv_freq = p.inv_freq;
-            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, grp, (sub == 3 && a.w13_flags) ? a.flags : nullptr, err, tacc, timing, a.dbg, [&](int row, int b, float v, int, bool valid) {
+            v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, grp, err, tacc, timing, a.dbg, [&](int row, int b, float v, int, bool valid) {
                 const float other = __shfl_xor_sync(0xffffffffu, v, NB);    /* row ^ 1 of the same column: RoPE pair / (gate, up) pair */
                 if (!valid) return;
                 switch (sub) {
@@ -834,18 +785,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 V2PROF();
                 v2_grid_barrier(a.bar, gen, err);
                 V2PROF();
-                v2_attention<NB>(a, sm, att_scr, layer, seq);
+                v2_attention<NB>(a, sm, att_scr, layer);
                 V2PROF();
-                if (!a.att_flags) v2_grid_barrier(a.bar, gen, err);   /* else: wo waits for the attention flags */
+                v2_grid_barrier(a.bar, gen, err);
                 V2PROF();
-            } else if (sub == 2 || sub == 6) {
+            } else if (sub == 2 || sub == 3 || sub == 6) {
                 V2PROF();
                 v2_grid_barrier(a.bar, gen, err);
                 if (sub != 6) V2PROF();
-            } else if (sub == 3) {
-                V2PROF();
-                if (!a.w13_flags) v2_grid_barrier(a.bar, gen, err);   /* else: w2 waits for the w1|w3 row counters */
-                V2PROF();
             }
         }
         {   /* per-CTA argmax per column: every warp ran some of the logits epilogues (its lanes' column is lane % NB) */
@@ -987,7 +934,6 @@ static int v2_alloc(VbEngine *e) {
     s->argmax = (unsigned long long *)vb_dev_alloc_owned(e, (size_t)e->sm_count * V2_MAXB * 8);
     s->bar = (unsigned int *)vb_dev_alloc_owned(e, 1024);    /* [0] grid barrier, [32] error word, [64..127] attention tickets */
     s->ctr = (unsigned int *)vb_dev_alloc_owned(e, (size_t)V2_MAX_STEPS * V2_SUBPHASES * 4);
-    s->flags = (unsigned int *)vb_dev_alloc_owned(e, 512);
     s->st = (VbDecState *)vb_dev_alloc_owned(e, sizeof(VbDecState) * V2_MAXB);
     s->logits_extra = (float *)vb_dev_alloc_owned(e, (size_t)(V2_MAXB - 1) * VOX_VOCAB_SIZE * 4);
     s->prof = NULL;
@@ -1046,15 +992,13 @@ extern "C" int vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb,
     for (int b = nb; b < V2_MAXB; b++) { a.col[b] = a.col[0]; a.col[b].n_steps = 0; }
     a.x = s->x; a.q = s->q; a.attn_out = s->attn_out; a.gate = s->gate;
     a.part_m = s->part_m; a.part_l = s->part_l; a.part_o = s->part_o; a.argmax = s->argmax;
-    a.bar = s->bar; a.ctr = s->ctr; a.flags = s->flags; a.st_out = s->st;
+    a.bar = s->bar; a.ctr = s->ctr; a.st_out = s->st;
     a.nb = nb; a.n_steps = n_steps; a.verify = verify;
     const char *ev;
     a.inflight_max = (ev = getenv("VOX_CUDA_V2_INFLIGHT")) ? atoi(ev) : 3;
     if (a.inflight_max < 1) a.inflight_max = 1;
     if (a.inflight_max > V2_SLOTS) a.inflight_max = V2_SLOTS;
     a.dynamic = (ev = getenv("VOX_CUDA_V2_DYNAMIC")) ? atoi(ev) : 1;
-    a.att_flags = (ev = getenv("VOX_CUDA_V2_ATTFLAGS")) ? atoi(ev) : 0;   /* 1: wo column blocks wait for per-(column, kv head) flags instead of a grid barrier after attention */
-    a.w13_flags = (ev = getenv("VOX_CUDA_V2_W13FLAGS")) ? atoi(ev) : 0;   /* 1: w2 column blocks wait for row counters instead of a grid barrier after w1|w3 */
     a.dbg = (ev = getenv("VOX_CUDA_V2_DBG")) ? atoi(ev) : 0;     /* diagnostics only (results are wrong): 1 = no FMAs, 2 = no reductions/epilogues */
     a.prof = NULL; a.prof_step = -1;
     if ((ev = getenv("VOX_CUDA_V2_PROF")) && n_steps > atoi(ev)) {
@@ -1063,7 +1007,6 @@ extern "C" int vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb,
         a.prof = s->prof; a.prof_step = atoi(ev);
     }
     if (cudaMemsetAsync(s->bar, 0, 1024, lead->stream) != cudaSuccess) return -1;
-    if (cudaMemsetAsync(s->flags, 0, 512, lead->stream) != cudaSuccess) return -1;
     if (cudaMemsetAsync(s->ctr, 0, (size_t)n_steps * V2_SUBPHASES * 4, lead->stream) != cudaSuccess) return -1;
     void *args[] = { &a };
     const void *fn = nb == 1 ? (const void *)k_dec_v2<1> : nb == 2 ? (const void *)k_dec_v2<2> : nb <= 4 ? (const void *)k_dec_v2<4> : (const void *)k_dec_v2<8>;

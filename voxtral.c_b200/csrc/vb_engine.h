@@ -93,7 +93,7 @@ typedef struct {
 typedef struct {
     float *x, *q, *attn_out, *gate, *part_m, *part_l, *part_o, *logits_extra;
     unsigned long long *argmax;
-    unsigned int *bar, *ctr, *flags;
+    unsigned int *bar, *ctr;
     VbDecState *st;
     long long *prof;
 } VbV2Scratch;
