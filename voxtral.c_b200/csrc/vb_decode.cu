@@ -413,7 +413,8 @@ extern "C" int vb_decoder_run_steps(VbEngine *e, const float *d_adapter, int ada
         VB_CUDA_OK(cudaMemcpyAsync(&st, driver == 5 ? e->v2.st : e->d_state, sizeof st, cudaMemcpyDeviceToHost, e->stream));
         cudaError_t serr = cudaStreamSynchronize(e->stream);
         if (serr != cudaSuccess) {
-            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s)\n", cudaGetErrorString(serr), driver == 1 ? "graph" : driver == 5 ? "v2" : "persist");
+            fprintf(stderr, "voxtral_b200: decode kernel failed: %s (mode %s, wait-guard code %d)\n", cudaGetErrorString(serr),
+                    driver == 1 ? "graph" : driver == 5 ? "v2" : "persist", driver == 5 && e->v2.err_host ? *e->v2.err_host : -1);
             vb_cuda_fail(serr, __FILE__, __LINE__);
         }
         VB_CUDA_OK(cudaMemcpy(e->h_tokens_pinned, e->d_tokens, (size_t)st.n_out * 4, cudaMemcpyDeviceToHost));

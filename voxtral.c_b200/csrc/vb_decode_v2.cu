@@ -64,6 +64,7 @@ struct V2Args {
     unsigned long long *argmax;                /* [grid][V2_MAXB] */
     unsigned int *bar;                         /* [0] grid barrier, [32] error word, [64 + column * 8 + kv head] attention tickets */
     unsigned int *ctr;                         /* [n_steps][V2_SUBPHASES] chunk counters of the dynamic phases */
+    int *err;                                  /* host-mapped word: which wait gave up (spin_guard code) -- survives the trap */
     VbDecState *st_out;                        /* [nb] */
     int nb, n_steps, inflight_max, dynamic, verify, dbg;
     long long *prof; int prof_step;
@@ -139,7 +140,7 @@ __device__ __forceinline__ void v2_static_rows(int total, int unit, int &r0, int
  * (A first version kept the state in a struct handed to a noinline function: ~30 local-memory accesses per chunk made the
  * producer, not HBM, the bottleneck at 17 B/cycle/SM.) */
 __device__ void v2_producer(V2Smem *sm, uint8_t *slots, const V2Args &a) {
-    int *err = (int *)(a.bar + 32);
+    int *err = a.err;
     uint32_t it = 0, landed = 0;
     const uint32_t inflight_max = (uint32_t)a.inflight_max;
     bool dead = false;
@@ -669,7 +670,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
     V2Smem *sm = reinterpret_cast<V2Smem *>(v2_smem_raw + (size_t)V2_SLOTS * V2_SLOT_BYTES + (size_t)V2_ATT_FLOATS * 4);
     const DecParams &p = a.p;
     const int tid = threadIdx.x, lane = tid & 31;
-    int *err = (int *)(a.bar + 32);
+    int *err = a.err;
 
     if (tid == 0) {
         for (int i = 0; i < V2_SLOTS; i++) { mbar_init(&sm->full[i], 1); mbar_init(&sm->empty[i], V2_CW); }
@@ -935,6 +936,7 @@ static int v2_alloc(VbEngine *e) {
     s->bar = (unsigned int *)vb_dev_alloc_owned(e, 1024);    /* [0] grid barrier, [32] error word, [64..127] attention tickets */
     s->ctr = (unsigned int *)vb_dev_alloc_owned(e, (size_t)V2_MAX_STEPS * V2_SUBPHASES * 4);
     s->st = (VbDecState *)vb_dev_alloc_owned(e, sizeof(VbDecState) * V2_MAXB);
+    if (cudaHostAlloc((void **)&s->err_host, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer((void **)&s->err_dev, s->err_host, 0) != cudaSuccess) { s->err_host = NULL; s->err_dev = (int *)(s->bar + 32); cudaGetLastError(); }
     s->logits_extra = (float *)vb_dev_alloc_owned(e, (size_t)(V2_MAXB - 1) * VOX_VOCAB_SIZE * 4);
     s->prof = NULL;
     e->weight_bytes = wb;
@@ -992,7 +994,8 @@ extern "C" int vb_decoder_v2_launch(VbEngine *lead, const VbV2Col *cols, int nb,
     for (int b = nb; b < V2_MAXB; b++) { a.col[b] = a.col[0]; a.col[b].n_steps = 0; }
     a.x = s->x; a.q = s->q; a.attn_out = s->attn_out; a.gate = s->gate;
     a.part_m = s->part_m; a.part_l = s->part_l; a.part_o = s->part_o; a.argmax = s->argmax;
-    a.bar = s->bar; a.ctr = s->ctr; a.st_out = s->st;
+    a.bar = s->bar; a.ctr = s->ctr; a.st_out = s->st; a.err = s->err_dev;
+    if (s->err_host) *s->err_host = 0;
     a.nb = nb; a.n_steps = n_steps; a.verify = verify;
     const char *ev;
     a.inflight_max = (ev = getenv("VOX_CUDA_V2_INFLIGHT")) ? atoi(ev) : 3;

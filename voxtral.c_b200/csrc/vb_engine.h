@@ -94,6 +94,7 @@ typedef struct {
     float *x, *q, *attn_out, *gate, *part_m, *part_l, *part_o, *logits_extra;
     unsigned long long *argmax;
     unsigned int *bar, *ctr;
+    int *err_host, *err_dev;                    /* pinned mapped word the kernel's wait guards report into */
     VbDecState *st;
     long long *prof;
 } VbV2Scratch;

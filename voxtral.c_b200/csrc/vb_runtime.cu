@@ -17,6 +17,8 @@ extern "C" { __thread jmp_buf *vb_err_jmp = NULL; }
 
 extern "C" void vb_cuda_fail(cudaError_t err, const char *file, int line) {
     fprintf(stderr, "voxtral_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err), file, line, cudaGetErrorString(err));
+    const char *logp = getenv("VOX_CUDA_ERRLOG");       /* test harnesses capture stderr: keep a copy where they cannot lose it */
+    if (logp) { FILE *f = fopen(logp, "a"); if (f) { fprintf(f, "CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err), file, line, cudaGetErrorString(err)); fclose(f); } }
     if (vb_err_jmp) longjmp(*vb_err_jmp, 1);
     abort();
 }
@@ -77,6 +79,7 @@ extern "C" void vb_device_shutdown(VbEngine *e) {
     if (!e->parent) { free(e->mirrors); e->mirrors = NULL; e->n_mirrors = 0; }
     for (int i = 0; i < VB_WS_SLOTS; i++) { cudaFree(e->ws[i]); e->ws[i] = NULL; e->ws_bytes[i] = 0; }
     cudaFree(e->d_dist_adapter); e->d_dist_adapter = NULL; e->dist_adapter_cap = 0;
+    if (e->v2.err_host) { cudaFreeHost(e->v2.err_host); e->v2.err_host = NULL; }
     if (e->step_graph_ready) cudaGraphExecDestroy(e->step_graph);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->ev_user0); cudaEventDestroy(e->ev_user1);

@@ -583,7 +583,7 @@ void vox_stream_free(vox_stream_t *s) {
                     s->n_generated > 1 ? gen_ms / (s->n_generated - 1) : 0);
         }
     }
-    vb_sync(s->e);
+    cudaStreamSynchronize(s->e->stream);                /* teardown never aborts: a failed context still frees its host state */
     vox_mel_free(s->mel);
     if (s->tokenizer) vox_tokenizer_free(s->tokenizer);
     cudaFree(s->d_adapter); cudaFree(s->d_mel_tail); cudaFree(s->d_conv0_tail);
@@ -644,6 +644,7 @@ int vox_cuda_streams_decode(vox_stream_t **ss, int n) {
         if (vb_decoder_v2_launch(lead, cols, nb, longest, 0, st) != 0) VB_FAIL("batched decode launch failed");
         VB_CUDA_OK(cudaEventRecord(e1, lead->stream));
         cudaError_t serr = cudaStreamSynchronize(lead->stream);
+        if (serr != cudaSuccess) fprintf(stderr, "vox_cuda_streams_decode: decode kernel failed (%d columns, wait-guard code %d)\n", nb, lead->v2.err_host ? *lead->v2.err_host : -1);
         VB_CUDA_OK(serr);
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
         int steps = 0;
