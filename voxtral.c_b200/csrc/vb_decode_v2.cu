@@ -776,7 +776,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                     break; }
                 case 3: if (!(row & 1)) a.gate[(size_t)b * VOX_DEC_HIDDEN + (row >> 1)] = vb_silu(v) * other; break;   /* voxtral_decoder.c:682-686 */
                 default: {
-                    sm->c_logits[b][row] = v;
+                    if (b < a.nb) sm->c_logits[b][row] = v;            /* (padding columns alias column 0's buffers) */
                     const unsigned long long c = pack_cand(v, row);
                     if (c > best) best = c;
                     break; }
