@@ -269,6 +269,119 @@ k_gemv_generic(float *__restrict__ y, const float *__restrict__ x, const uint16_
         [&](int row, float v, int, bool valid) { if (valid) y[row] = bias ? v + bias[row] : v; });
 }
 
+/* Small-M linears (2 <= M < 8: the live-stream encoder calls of main.c's -I 0.1 mode, where a call has ~5 positions):
+ * the same streaming GEMV core with MB activation rows in registers, so the weights are read ONCE, coalesced, by all SMs,
+ * instead of going through a 64x64-tile GEMM whose grid is a fraction of the machine (measured: 33 ms per 5-position encoder
+ * call before, see profiles/r02_live.md).  y[m][row] = W[row,:] . x[m] (+bias) with the GEMM epilogues of vb_ops.cuh;
+ * 16 / MB rows per batch so that a batch always reduces 16 (row, m) values.  C and A are row-major with pitches ldc / lda. */
+template <int CPT, int MB, int EPI>
+__global__ void __launch_bounds__(DT, 1)
+k_gemv_cols(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda, const uint16_t *__restrict__ W,
+            const float *__restrict__ bias, int K, int N, int NT, int M) {
+    constexpr int R = 16 / MB;                                    /* rows per batch */
+    __shared__ float red[2][DW][16];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool active = t < NT;
+    float xr[MB][CPT * 8];
+#pragma unroll
+    for (int m = 0; m < MB; m++)
+#pragma unroll
+        for (int c = 0; c < CPT; c++) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (active && m < M) {
+                const float4 *p = reinterpret_cast<const float4 *>(A + (size_t)m * lda + (size_t)(c * NT + t) * 8);
+                a = p[0]; b = p[1];
+            }
+            xr[m][c * 8 + 0] = a.x; xr[m][c * 8 + 1] = a.y; xr[m][c * 8 + 2] = a.z; xr[m][c * 8 + 3] = a.w;
+            xr[m][c * 8 + 4] = b.x; xr[m][c * 8 + 5] = b.y; xr[m][c * 8 + 6] = b.z; xr[m][c * 8 + 7] = b.w;
+        }
+    int u0, nu; cta_rows(N / 2, u0, nu);                          /* row pairs: SwiGLU keeps (gate, up) in one CTA */
+    const int row0 = u0 * 2, nrows = nu * 2;
+    const uint16_t *wt = W + (size_t)t * 8;
+    int buf = 0;
+    for (int rb = 0; rb < nrows; rb += R) {
+        float acc[16];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            uint4 w[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; c++)
+                w[c] = (active && rb + r < nrows) ? ldg_stream16(wt + (size_t)(row0 + rb + r) * K + (size_t)c * NT * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int m = 0; m < MB; m++) {
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < CPT; c++) a = dot8(w[c], &xr[m][c * 8], a);
+                acc[r * MB + m] = a;
+            }
+        }
+        const float tot = warp_transpose_reduce<16>(acc, lane);
+        if (!(lane & 1)) red[buf][warp][lane >> 1] = tot;
+        __syncthreads();
+        if (warp == 0) {
+            float v = 0.f;
+            if (lane < 16) {
+#pragma unroll
+                for (int wv = 0; wv < DW; wv++) v += red[buf][wv][lane];
+            }
+            const int r = lane / MB, m = lane % MB, row = row0 + rb + r;
+            const float other = __shfl_xor_sync(0xffffffffu, v, MB);       /* row ^ 1, same m: the (gate, up) partner */
+            if (lane < 16 && rb + r < nrows && m < M) {
+                if (EPI == VB_EPI_SWIGLU) {
+                    if (!(row & 1)) C[(size_t)m * ldc + (row >> 1)] = vb_silu(v) * other;
+                } else {
+                    if (bias) v += bias[row];
+                    if (EPI == VB_EPI_GELU) v = vb_gelu_tanh(v);
+                    if (EPI == VB_EPI_RESIDUAL) v += C[(size_t)m * ldc + row];
+                    C[(size_t)m * ldc + row] = v;
+                }
+            }
+        }
+        buf ^= 1;
+    }
+}
+
+template <int CPT, int MB>
+static void gemv_cols_launch(VbEngine *e, float *C, int ldc, const float *A, int lda, const uint16_t *W, const float *bias,
+                             int K, int N, int NT, int M, int epi) {
+    const int G = e->sm_count;
+    switch (epi) {
+    case VB_EPI_STORE:    k_gemv_cols<CPT, MB, VB_EPI_STORE><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M); break;
+    case VB_EPI_GELU:     k_gemv_cols<CPT, MB, VB_EPI_GELU><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M); break;
+    case VB_EPI_RESIDUAL: k_gemv_cols<CPT, MB, VB_EPI_RESIDUAL><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M); break;
+    case VB_EPI_SWIGLU:   k_gemv_cols<CPT, MB, VB_EPI_SWIGLU><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M); break;
+    }
+}
+
+/* returns 0 if the shape is not covered (the caller falls back to the tiled GEMM) */
+extern "C" int vb_gemv_cols_dev(VbEngine *e, const float *A, int lda, const uint16_t *W, const float *bias, float *C, int ldc,
+                                int M, int N, int K, int epi) {
+    if (M < 1 || M > 8 || (K % 8) || (N % 2) || (lda % 4)) return 0;
+    const int chunks = K / 8;
+    int cpt = 1;
+    while (cpt <= 2 && (chunks % cpt || chunks / cpt > DT)) cpt++;
+    if (cpt > 2) return 0;
+    const int NT = chunks / cpt;
+    const int per = cpt == 1 ? 8 : 4;                             /* activation rows per launch (register budget) */
+    for (int m0 = 0; m0 < M; m0 += per) {
+        const int mb = M - m0 < per ? M - m0 : per;
+        const float *a = A + (size_t)m0 * lda; float *c = C + (size_t)m0 * ldc;
+        if (cpt == 1) {
+            if (mb <= 1) gemv_cols_launch<1, 1>(e, c, ldc, a, lda, W, bias, K, N, NT, mb, epi);
+            else if (mb <= 2) gemv_cols_launch<1, 2>(e, c, ldc, a, lda, W, bias, K, N, NT, mb, epi);
+            else if (mb <= 4) gemv_cols_launch<1, 4>(e, c, ldc, a, lda, W, bias, K, N, NT, mb, epi);
+            else gemv_cols_launch<1, 8>(e, c, ldc, a, lda, W, bias, K, N, NT, mb, epi);
+        } else {
+            if (mb <= 1) gemv_cols_launch<2, 1>(e, c, ldc, a, lda, W, bias, K, N, NT, mb, epi);
+            else if (mb <= 2) gemv_cols_launch<2, 2>(e, c, ldc, a, lda, W, bias, K, N, NT, mb, epi);
+            else gemv_cols_launch<2, 4>(e, c, ldc, a, lda, W, bias, K, N, NT, mb, epi);
+        }
+        VB_CUDA_OK(cudaGetLastError());
+        vb_launch_count(e, 1);
+    }
+    return 1;
+}
+
 /* ---------------------------------------------------------------- host side */
 DecParams vb_make_dec_params(VbEngine *e, int use_embed_kernel) {
     DecParams p;

@@ -224,6 +224,7 @@ void vb_build_prompt_dev(VbEngine *e, float *d_out, const float *d_adapter, int 
 void vb_conv_stem_full_dev(VbEngine *e, const float *d_mel, int mel_frames, float *d_out, int *out_len);
 void vb_conv_stem_range_dev(VbEngine *e, const float *d_mel, int mel_frames, int p0, int p1, float *d_out);
 void vb_gemv_bf16_dev(VbEngine *e, float *y, const float *x, const uint16_t *W, const float *bias, int K, int N);
+int  vb_gemv_cols_dev(VbEngine *e, const float *A, int lda, const uint16_t *W, const float *bias, float *C, int ldc, int M, int N, int K, int epi);
 
 #ifdef __cplusplus
 }

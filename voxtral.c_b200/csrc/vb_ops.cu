@@ -139,6 +139,8 @@ void vb_gemm_bf16w(VbEngine *e, const float *A, int lda, const uint16_t *W, cons
     if (M <= 0 || N <= 0) return;
     if (gemm_use_tc() && M >= 8 && vb_gemm_tc_usable(M, N, K) && (lda % 4) == 0 && (ldc % 4) == 0)
         vb_gemm_tc(e, A, lda, W, bias, C, ldc, M, N, K, epi);
+    else if (gemm_use_tc() && M < 8 && vb_gemv_cols_dev(e, A, lda, W, bias, C, ldc, M, N, K, epi))
+        return;                                              /* a handful of rows: stream the weights once, GEMV style */
     else
         gemm_dispatch<uint16_t>(e, A, lda, W, bias, C, ldc, M, N, K, epi);
 }
