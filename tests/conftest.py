@@ -93,6 +93,9 @@ class RefLib:
             "vox_tokenizer_free": (None, [vp]),
             "vox_decoder_forward": (i, [vp, fp, fp]), "vox_decoder_prefill": (None, [vp, fp, i]),
             "vox_encoder_forward_incremental": (fp, [vp, fp, i, ip]),
+            "vox_encoder_forward": (fp, [vp, fp, i, ip]),
+            "vox_copy": (None, [fp, fp, i]), "vox_matmul_t": (None, [fp, fp, fp, i, i, i]),
+            "vox_linear_nobias": (None, [fp, fp, fp, i, i, i]), "vox_matmul_t_bf16": (None, [fp, fp, u16p, i, i, i]),
             "vox_adapter_forward": (fp, [vp, fp, i, ip]),
         }
         for n, (r, a) in sig.items():

@@ -78,6 +78,8 @@ def test_rms_norm(vb, ref, rows, hidden):
     (1, 3072, 4096, False), (1, 3072, 1024, False), (1, 4096, 3072, False), (1, 9216, 3072, False),
     (1, 3072, 9216, False), (1, 1280, 2048, True), (1, 5120, 1280, True),
     (38, 3072, 1024, False), (5, 1280, 2048, True), (130, 2048, 1280, True), (3, 384, 70, True),
+    # 2 <= M < 8: the live-stream encoder calls go through the multi-row streaming GEMV (vb_gemv_cols_dev)
+    (2, 3072, 3072, False), (6, 2048, 1280, True), (7, 5120, 1280, True), (4, 3840, 1280, True), (8, 1280, 6144, True),
 ])
 def test_linear_bf16(vb, ref, M, K, N, bias):
     rng = np.random.default_rng(4 + M + K + N)
@@ -92,6 +94,35 @@ def test_linear_bf16(vb, ref, M, K, N, bias):
     # bf16 activation planes) but the tcgen05 accumulator does not round like an IEEE FMA chain -> ~1e-5 of the row scale
     # (measured 1.1e-5 at K=3072, identical with 2 or 3 planes), so 3e-5.
     close(ya, yb, 1e-5 if M == 1 else 3e-5)
+
+
+def test_remaining_kernel_surface_symbols(vb, ref):
+    """vox_copy, vox_matmul_t, vox_linear_nobias, vox_matmul_t_bf16 (voxtral_kernels.c:42-48,71-86,106-121,255-263): exported
+    for header completeness, no pipeline caller; same host-pointer semantics as the reference."""
+    rng = np.random.default_rng(55)
+    L, R = vb.lib(), ref.L
+    for fn in ("vox_copy", "vox_matmul_t", "vox_linear_nobias", "vox_matmul_t_bf16"):
+        getattr(L, fn).restype = None
+    L.vox_copy.argtypes = [fp, fp, C.c_int]
+    L.vox_matmul_t.argtypes = [fp, fp, fp, C.c_int, C.c_int, C.c_int]
+    L.vox_linear_nobias.argtypes = [fp, fp, fp, C.c_int, C.c_int, C.c_int]
+    L.vox_matmul_t_bf16.argtypes = [fp, fp, u16p, C.c_int, C.c_int, C.c_int]
+    src = rng.normal(size=1000).astype(np.float32); a = np.zeros_like(src); b = np.zeros_like(src)
+    L.vox_copy(P(a), P(src), src.size); R.vox_copy(P(b), P(src), src.size)
+    assert np.array_equal(a, src) and np.array_equal(b, src)
+    M, K, N = 7, 200, 33
+    A = rng.normal(size=(M, K)).astype(np.float32); B = rng.normal(size=(N, K)).astype(np.float32)
+    ya, yb = np.empty((M, N), np.float32), np.empty((M, N), np.float32)
+    L.vox_matmul_t(P(ya), P(A), P(B), M, K, N); R.vox_matmul_t(P(yb), P(A), P(B), M, K, N)
+    close(ya, yb, 1e-5)
+    L.vox_linear_nobias(P(ya), P(A), P(B), M, K, N); R.vox_linear_nobias(P(yb), P(A), P(B), M, K, N)
+    close(ya, yb, 1e-5)
+    for M2, K2, N2 in ((1, 1280, 256), (9, 1280, 256), (5, 2048, 130)):
+        A2 = rng.normal(size=(M2, K2)).astype(np.float32); W = bf16_weights(rng, N2, K2, np.sqrt(3.0 / K2))
+        za, zb = np.empty((M2, N2), np.float32), np.empty((M2, N2), np.float32)
+        L.vox_matmul_t_bf16(P(za), P(A2), W.ctypes.data_as(u16p), M2, K2, N2)
+        R.vox_matmul_t_bf16(P(zb), P(A2), W.ctypes.data_as(u16p), M2, K2, N2)
+        close(za, zb, 3e-5)
 
 
 def test_linear_f32_and_matmul(vb, ref):
