@@ -4,9 +4,9 @@
  * issued on the engine's own stream -- there is no host synchronisation inside the layer loop.
  *
  * The encoder is exact under sharding: rank r owns a contiguous, 4-aligned range [p0, p1) of encoder positions.
- *   mel           every rank computes the (cheap, 37 MFLOP per audio second) mel frames of the whole recording
- *   conv stem     only the rank's own rows: conv1 output j reads conv0 rows 2j-1..2j+1, conv0 row i reads mel frames
- *                 i-2..i -- a 3-frame halo that the rank recomputes locally (voxtral.c:537-715 on a slice)
+ *   mel, conv     only the rank's own rows: conv1 output j reads conv0 rows 2j-1..2j+1, conv0 row i reads mel frames i-2..i,
+ *                 frame t reads 400 samples at 160 t of the padded signal -- a 3-frame halo that the rank recomputes locally,
+ *                 so only its slice of the PCM crosses PCIe (voxtral_audio.c:454-513, voxtral.c:537-715 on a slice)
  *   layer l       [RMSNorm -> wq|wk|wv -> RoPE at GLOBAL positions] for the own rows, then rank r sends its LAST 750
  *                 K and V rows to rank r+1 (ncclSend/ncclRecv in one group): that is all the window-750 attention of
  *                 the next rank can see across the boundary (voxtral_encoder.c:388-406), and layer-l K/V of a position
@@ -120,7 +120,7 @@ enum { WSD_X = VB_WS_DIST_X, WSD_KB = VB_WS_DIST_X + 1, WSD_VB = VB_WS_DIST_X + 
 
 /* Complete recording -> this rank's adapter rows are computed, all ranks' rows are gathered: *d_adapter_out ([T,3072] f32,
  * device memory owned by the ctx, valid until the next call) holds all T adapter rows in position order on EVERY rank.
- * pcm: host mono 16 kHz, the whole recording (each rank reads only what its mel needs: everything, today).
+ * pcm: host mono 16 kHz, the whole recording (each rank reads only the slice its own frames need).
  * encode_ms: device time of the call on this rank (CUDA events on the engine's stream), max it over ranks yourself.
  * Works with world == 1 (no NCCL needed): the same code path unsharded -- the comparison baseline. */
 int vox_cuda_encode_sharded(vox_ctx_t *ctx, const float *pcm, int n_samples, float **d_adapter_out, int *n_tokens,
@@ -133,14 +133,8 @@ int vox_cuda_encode_sharded(vox_ctx_t *ctx, const float *pcm, int n_samples, flo
     VB_CUDA_OK(cudaSetDevice(e->device));
     VB_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
 
-    /* mel of the whole recording, exactly as the stream path sees it: left pad, flush padding, finish (voxtral.c:1203,1593-1606) */
-    vox_mel_ctx_t *mel = vb_mel_ctx_init_on(e, 32 * 1280);
-    vox_mel_feed(mel, pcm, n_samples);
-    const int align = (1280 - n_samples % 1280) % 1280;
-    vb_mel_feed_zeros(mel, align + (ctx->delay_tokens + 1 + 10) * 1280);
-    vox_mel_finish(mel, 0);
-    int F = 0, f_off = 0;
-    float *d_mel = vb_mel_dev_frames(mel, &F, &f_off);
+    /* the recording's frame count as the stream path would produce it (left pad, flush padding, finish: voxtral.c:1203,1593-1606) */
+    const int F = vb_mel_recording_frames(n_samples, ctx->delay_tokens);
     const int P = F / 2;                                   /* stream path: an odd last frame never gets a partner */
     int p0, p1, h;
     vox_cuda_shard_plan(P, world, rank, &p0, &p1, &h);
@@ -149,19 +143,23 @@ int vox_cuda_encode_sharded(vox_ctx_t *ctx, const float *pcm, int n_samples, flo
         int q0, q1;
         for (int r = 0; r < world; r++) {
             vox_cuda_shard_plan(P, world, r, &q0, &q1, NULL);
-            if (q1 - q0 < VOX_ENC_WINDOW) { fprintf(stderr, "vox_cuda_encode_sharded: recording too short for %d ranks (every shard must hold one attention window)\n", world); vox_mel_free(mel); VB_API_END; return -1; }
+            if (q1 - q0 < VOX_ENC_WINDOW) { fprintf(stderr, "vox_cuda_encode_sharded: recording too short for %d ranks (every shard must hold one attention window)\n", world); VB_API_END; return -1; }
         }
     }
 
-    /* conv stem of rows [p0, p1) only */
+    /* mel frames and conv stem of the rank's own positions only: conv1 output j needs mel frames 2j-3..2j+1, so the rank reads
+     * just its slice of the PCM (plus a 3-frame halo it recomputes) */
     float *x = vb_ws(e, WSD_X, (size_t)(M > 0 ? M : 1) * VOX_ENC_DIM * 4);
-    vb_conv_stem_range_dev(e, d_mel, F, p0, p1, x);
-    VB_CUDA_OK(cudaStreamSynchronize(e->stream));         /* the mel context owns d_mel */
-    vox_mel_free(mel);
-
-    /* 32 layers with a K/V halo exchange between the two halves of each */
     float *kb = vb_ws(e, WSD_KB, (size_t)(h + M) * VB_ENC_ATT * 4);
     float *vv = vb_ws(e, WSD_VB, (size_t)(h + M) * VB_ENC_ATT * 4);
+    {
+        const int f0 = 2 * p0 - 3 > 0 ? 2 * p0 - 3 : 0, f1 = 2 * p1;
+        float *d_mel = kb;                                 /* (2M+3) x 128 floats fit in the K scratch, which layer 0 fills later */
+        vb_mel_recording_range(e, pcm, n_samples, f0, f1, d_mel);
+        vb_conv_stem_range_dev(e, d_mel, f0, F, p0, p1, x);
+    }
+
+    /* 32 layers with a K/V halo exchange between the two halves of each */
     int nxt = 0;                                          /* rows the right neighbour needs from this rank */
     if (rank + 1 < world) vox_cuda_shard_plan(P, world, rank + 1, NULL, NULL, &nxt);
     for (int l = 0; l < VOX_ENC_LAYERS; l++) {

@@ -10,9 +10,12 @@
  *
  * Encoder KV: the reference keeps a growing f32 cache that it compacts to the last 750
  * positions before every call (voxtral_encoder.c:388-406,463-466).  Only those 750 rows can
- * ever be attended again, so HBM holds exactly that: a [32][750][2048] tail per K and V.
- * Within a call, layer l works on a scratch [cache_len + new_len][2048] K/V buffer whose
- * prefix is the tail; afterwards the last <=750 rows become the new tail.
+ * ever be attended again.  HBM holds a [32][750 + 2048][2048] cache per K and V:
+ *   - small calls (<= 1024 new positions: every live-stream call) APPEND their K/V rows in place
+ *     and attend over [last <=750 rows | new rows] of the cache; when the cache is full the last
+ *     750 rows move to the front (once per ~400 live calls) -- no per-call copies;
+ *   - large one-shot calls work on a scratch [cache_len + new_len][2048] buffer whose prefix is
+ *     the cached tail; afterwards the last <=750 rows become the cache content.
  */
 #include "vb_ops.cuh"
 #include <string.h>
@@ -21,9 +24,12 @@
 #define ENC_HID VOX_ENC_HIDDEN
 #define ENC_WIN VOX_ENC_WINDOW
 
+#define ENC_APPEND_MAX 1024                                   /* calls up to this many positions append in place */
+#define ENC_CACHE_ROWS (ENC_WIN + 2048)                       /* rows per layer in the K / V cache */
+
 static void enc_alloc_tail(VbEngine *e) {
     if (e->d_enc_tail_k) return;
-    size_t bytes = (size_t)VOX_ENC_LAYERS * ENC_WIN * VB_ENC_ATT * sizeof(float);
+    size_t bytes = (size_t)VOX_ENC_LAYERS * ENC_CACHE_ROWS * VB_ENC_ATT * sizeof(float);
     const size_t wb = e->weight_bytes;
     e->d_enc_tail_k = (float *)vb_dev_alloc_owned(e, bytes);
     e->d_enc_tail_v = (float *)vb_dev_alloc_owned(e, bytes);
@@ -67,28 +73,50 @@ extern "C" void vb_enc_layer_rest_dev(VbEngine *e, int l, float *x, int M, const
 extern "C" void vb_encoder_layers_dev(VbEngine *e, float *x, int M, int cache_len, int logical_start, int update_tail) {
     if (M <= 0) return;
     enc_alloc_tail(e);
-    const int total = cache_len + M;
-    float *kb  = vb_ws(e, 5, (size_t)total * VB_ENC_ATT * 4);
-    float *vb  = vb_ws(e, 6, (size_t)total * VB_ENC_ATT * 4);
     const size_t row = (size_t)VB_ENC_ATT * sizeof(float);
-    const int keep = total < ENC_WIN ? total : ENC_WIN;
+    const size_t layer_rows = (size_t)ENC_CACHE_ROWS * VB_ENC_ATT;
+    if (cache_len == 0 && update_tail) e->enc_tail_len = 0;   /* a fresh stream (vox_stream_init / vox_cuda_reset_caches); the cache-less full forward leaves it alone */
+    int phys = e->enc_tail_len;                               /* rows valid at the front of every layer's cache */
+    const int p = cache_len < phys ? cache_len : phys;        /* prior rows the window can still see (<= 750) */
 
-    for (int l = 0; l < VOX_ENC_LAYERS; l++) {
-        float *tk = e->d_enc_tail_k + (size_t)l * ENC_WIN * VB_ENC_ATT;
-        float *tv = e->d_enc_tail_v + (size_t)l * ENC_WIN * VB_ENC_ATT;
-        if (cache_len > 0) {
-            VB_CUDA_OK(cudaMemcpyAsync(kb, tk, cache_len * row, cudaMemcpyDeviceToDevice, e->stream));
-            VB_CUDA_OK(cudaMemcpyAsync(vb, tv, cache_len * row, cudaMemcpyDeviceToDevice, e->stream));
+    if (update_tail && M <= ENC_APPEND_MAX) {
+        /* ---- append in place ---- */
+        if (phys + M > ENC_CACHE_ROWS) {                      /* full: keep the last p rows (source and destination cannot overlap) */
+            for (int l = 0; l < VOX_ENC_LAYERS; l++) {
+                float *ck = e->d_enc_tail_k + l * layer_rows, *cv = e->d_enc_tail_v + l * layer_rows;
+                VB_CUDA_OK(cudaMemcpyAsync(ck, ck + (size_t)(phys - p) * VB_ENC_ATT, p * row, cudaMemcpyDeviceToDevice, e->stream));
+                VB_CUDA_OK(cudaMemcpyAsync(cv, cv + (size_t)(phys - p) * VB_ENC_ATT, p * row, cudaMemcpyDeviceToDevice, e->stream));
+            }
+            phys = p;
         }
-        vb_enc_layer_qkv_dev(e, l, x, M, logical_start, kb, vb, cache_len);
-        vb_enc_layer_rest_dev(e, l, x, M, kb, vb, cache_len);
-        /* new tail = last `keep` rows of this layer's K/V */
-        if (!update_tail) continue;
-        VB_CUDA_OK(cudaMemcpyAsync(tk, kb + (size_t)(total - keep) * VB_ENC_ATT, keep * row, cudaMemcpyDeviceToDevice, e->stream));
-        VB_CUDA_OK(cudaMemcpyAsync(tv, vb + (size_t)(total - keep) * VB_ENC_ATT, keep * row, cudaMemcpyDeviceToDevice, e->stream));
+        for (int l = 0; l < VOX_ENC_LAYERS; l++) {
+            float *kb = e->d_enc_tail_k + l * layer_rows + (size_t)(phys - p) * VB_ENC_ATT;
+            float *vb = e->d_enc_tail_v + l * layer_rows + (size_t)(phys - p) * VB_ENC_ATT;
+            vb_enc_layer_qkv_dev(e, l, x, M, logical_start, kb, vb, p);      /* new rows land at cache rows [phys, phys + M) */
+            vb_enc_layer_rest_dev(e, l, x, M, kb, vb, p);
+        }
+        e->enc_tail_len = phys + M;
+    } else {
+        /* ---- one-shot: scratch [p + M] rows per layer, then the last <= 750 rows become the cache ---- */
+        const int total = p + M;
+        float *kb  = vb_ws(e, 5, (size_t)total * VB_ENC_ATT * 4);
+        float *vb  = vb_ws(e, 6, (size_t)total * VB_ENC_ATT * 4);
+        const int keep = total < ENC_WIN ? total : ENC_WIN;
+        for (int l = 0; l < VOX_ENC_LAYERS; l++) {
+            float *tk = e->d_enc_tail_k + l * layer_rows, *tv = e->d_enc_tail_v + l * layer_rows;
+            if (p > 0) {
+                VB_CUDA_OK(cudaMemcpyAsync(kb, tk + (size_t)(phys - p) * VB_ENC_ATT, p * row, cudaMemcpyDeviceToDevice, e->stream));
+                VB_CUDA_OK(cudaMemcpyAsync(vb, tv + (size_t)(phys - p) * VB_ENC_ATT, p * row, cudaMemcpyDeviceToDevice, e->stream));
+            }
+            vb_enc_layer_qkv_dev(e, l, x, M, logical_start, kb, vb, p);
+            vb_enc_layer_rest_dev(e, l, x, M, kb, vb, p);
+            if (!update_tail) continue;
+            VB_CUDA_OK(cudaMemcpyAsync(tk, kb + (size_t)(total - keep) * VB_ENC_ATT, keep * row, cudaMemcpyDeviceToDevice, e->stream));
+            VB_CUDA_OK(cudaMemcpyAsync(tv, vb + (size_t)(total - keep) * VB_ENC_ATT, keep * row, cudaMemcpyDeviceToDevice, e->stream));
+        }
+        if (update_tail) e->enc_tail_len = keep;
     }
     vb_rmsnorm_rows(e, x, x, e->d_enc_norm, nullptr, M, ENC_DIM, VOX_ENC_NORM_EPS);
-    if (update_tail) e->enc_tail_len = keep;
 }
 
 /* [enc_len,1280] -> [enc_len/4,3072]: the 4x "reshape" is free on row-major data

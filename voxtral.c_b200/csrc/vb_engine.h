@@ -151,8 +151,8 @@ typedef struct VbEngine {
 
     /* ---- M>1 scratch (prefill / encoder / adapter) ---- */
     float *ws[VB_WS_SLOTS]; size_t ws_bytes[VB_WS_SLOTS];         /* grow-on-demand workspaces */
-    float *d_enc_tail_k, *d_enc_tail_v;         /* [32][750][2048] */
-    int enc_tail_len;                           /* rows valid in the tail (<=750) */
+    float *d_enc_tail_k, *d_enc_tail_v;         /* [32][750 + 2048][2048]: the encoder K / V cache (vb_encoder.cu) */
+    int enc_tail_len;                           /* rows valid at the front of every layer's cache */
 
     /* ---- statistics ---- */
     unsigned long long launches;
@@ -213,6 +213,8 @@ vox_mel_ctx_t *vb_mel_ctx_init_on(VbEngine *e, int left_pad_samples);
 int    vb_mel_feed_zeros(vox_mel_ctx_t *c, int n);
 int    vb_mel_feed_device(vox_mel_ctx_t *c, const float *d_samples, int n);
 float *vb_mel_dev_frames(vox_mel_ctx_t *c, int *n_frames, int *frame_offset);
+int    vb_mel_recording_frames(int n_samples, int delay_tokens);
+void   vb_mel_recording_range(VbEngine *e, const float *pcm_host, int n_samples, int f0, int f1, float *d_out);
 
 /* vb_stream_dev.cu */
 void vb_d2d(VbEngine *e, void *dst, const void *src, size_t bytes);
@@ -222,7 +224,7 @@ void vb_d2h_sync(VbEngine *e, void *dst, const void *src, size_t bytes);
 void vb_sync(VbEngine *e);
 void vb_build_prompt_dev(VbEngine *e, float *d_out, const float *d_adapter, int n, int bos, int pad);
 void vb_conv_stem_full_dev(VbEngine *e, const float *d_mel, int mel_frames, float *d_out, int *out_len);
-void vb_conv_stem_range_dev(VbEngine *e, const float *d_mel, int mel_frames, int p0, int p1, float *d_out);
+void vb_conv_stem_range_dev(VbEngine *e, const float *d_mel, int mel_first, int mel_frames, int p0, int p1, float *d_out);
 void vb_gemv_bf16_dev(VbEngine *e, float *y, const float *x, const uint16_t *W, const float *bias, int K, int N);
 int  vb_gemv_cols_dev(VbEngine *e, const float *A, int lda, const uint16_t *W, const float *bias, float *C, int ldc, int M, int N, int K, int epi);
 

@@ -376,3 +376,31 @@ float *vox_mel_spectrogram(const float *samples, int n_samples, int *out_frames)
 }
 
 }  /* extern "C" */
+
+/* ---- frames [f0, f1) of a COMPLETE recording, as the stream path would produce them (vb_dist.c) ----
+ * The padded signal the stream path builds for a whole recording is [200 + 32*1280 zeros | pcm | align + (delay+1+10)*1280 zeros |
+ * 200 reflected samples (= zeros: they mirror the zero padding)] (voxtral.c:1203,1593-1606; voxtral_audio.c:544-545,602-629) and
+ * frame t reads padded samples [160 t, 160 t + 400).  A rank of a sequence-sharded run needs only its own frames, so only its
+ * slice of the PCM crosses PCIe. */
+extern "C" int vb_mel_recording_frames(int n_samples, int delay_tokens) {
+    const long long align = (1280 - n_samples % 1280) % 1280;
+    const long long total = 200 + 32 * 1280 + (long long)n_samples + align + (long long)(delay_tokens + 1 + 10) * 1280 + 200;
+    return (int)((total - N_FFT) / HOP + 1 - 1);                      /* the last frame is dropped (voxtral_audio.c:627-628) */
+}
+
+extern "C" void vb_mel_recording_range(VbEngine *e, const float *pcm_host, int n_samples, int f0, int f1, float *d_out) {
+    if (f1 <= f0) return;
+    const MelTables *tab = mel_tables(e->device);
+    const long long left = 200 + 32 * 1280;
+    const long long s0 = (long long)f0 * HOP, s1 = (long long)(f1 - 1) * HOP + N_FFT;   /* padded samples [s0, s1) */
+    const size_t len = (size_t)(s1 - s0);
+    float *ds = vb_ws(e, 9, len * 4);
+    VB_CUDA_OK(cudaMemsetAsync(ds, 0, len * 4, e->stream));
+    long long a = s0 > left ? s0 : left, b = s1 < left + n_samples ? s1 : left + n_samples;   /* the part that is real audio */
+    if (b > a) VB_CUDA_OK(cudaMemcpyAsync(ds + (a - s0), pcm_host + (a - left), (size_t)(b - a) * 4, cudaMemcpyHostToDevice, e->stream));
+    const int n = f1 - f0, blocks = (n + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA;
+    k_mel_frames<<<blocks, 256, 0, e->stream>>>(ds, 0, n, tab->cosT, tab->sinT, tab->filtT, tab->window, d_out);
+    VB_CUDA_OK(cudaGetLastError());
+    e->launches++;
+}
+

@@ -55,9 +55,10 @@ extern "C" void vb_conv_stem_full_dev(VbEngine *e, const float *d_mel, int F, fl
 
 /* Conv stem of encoder positions [p0, p1) only (stream semantics: P = F/2 positions, left zero padding at the start of the
  * recording): conv1 output j reads conv0 rows 2j-1..2j+1, conv0 row i reads mel frames i-2..i, so the slice needs mel frames
- * 2*p0-3 .. 2*p1-1 -- a 3-frame halo recomputed locally by a sequence-sharded run (vb_dist.c).  Row for row the same GEMM
- * arithmetic as the whole-sequence stem.  d_out: [p1-p0, 1280]. */
-extern "C" void vb_conv_stem_range_dev(VbEngine *e, const float *d_mel, int F, int p0, int p1, float *d_out) {
+ * 2*p0-3 .. 2*p1-1 -- a 3-frame halo recomputed locally by a sequence-sharded run (vb_dist.c).  d_mel holds frames
+ * [mel_first, ...) of the recording (mel_first = max(0, 2*p0-3) is enough).  Row for row the same GEMM arithmetic as the
+ * whole-sequence stem.  d_out: [p1-p0, 1280]. */
+extern "C" void vb_conv_stem_range_dev(VbEngine *e, const float *d_mel, int mel_first, int F, int p0, int p1, float *d_out) {
     const int M = p1 - p0;
     if (M <= 0 || 2 * p1 - 1 > F - 1) return;
     const int c_start = 2 * p0 - 1, n0 = 2 * M + 1;                 /* conv0 rows [c_start, c_start + n0) */
@@ -65,7 +66,7 @@ extern "C" void vb_conv_stem_range_dev(VbEngine *e, const float *d_mel, int F, i
     const int neg = m_start < 0 ? -m_start : 0;
     float *in0 = vb_ws(e, 10, (size_t)nm * VOX_MEL_BINS * 4);
     if (neg) vb_dzero(e, in0, (size_t)neg * VOX_MEL_BINS * 4);
-    vb_d2d(e, in0 + (size_t)neg * VOX_MEL_BINS, d_mel + (size_t)(m_start + neg) * VOX_MEL_BINS, (size_t)(nm - neg) * VOX_MEL_BINS * 4);
+    vb_d2d(e, in0 + (size_t)neg * VOX_MEL_BINS, d_mel + (size_t)(m_start + neg - mel_first) * VOX_MEL_BINS, (size_t)(nm - neg) * VOX_MEL_BINS * 4);
     float *c0 = vb_ws(e, 11, (size_t)n0 * VOX_ENC_DIM * 4);
     vb_conv_view_dev(e, in0, VOX_MEL_BINS, 1, n0, e->d_conv0_wk, e->d_conv0_b, c0, VOX_ENC_DIM);
     if (c_start < 0) vb_dzero(e, c0, (size_t)VOX_ENC_DIM * 4);      /* conv1's left zero pad row, not conv0 of zeros */
