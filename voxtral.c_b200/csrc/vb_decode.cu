@@ -298,46 +298,54 @@ k_gemv_cols(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda
     int u0, nu; cta_rows(N / 2, u0, nu);                          /* row pairs: SwiGLU keeps (gate, up) in one CTA */
     const int row0 = u0 * 2, nrows = nu * 2;
     const uint16_t *wt = W + (size_t)t * 8;
+    /* U batches of R rows are loaded up front (8 rows = 128 bytes per thread in flight for CPT = 1: with MB = 8 a single batch would
+     * be 2 rows and the kernel latency-bound), then reduced one after the other */
+    constexpr int U = CPT == 1 ? (8 / R > 0 ? 8 / R : 1) : 1;
     int buf = 0;
-    for (int rb = 0; rb < nrows; rb += R) {
-        float acc[16];
+    for (int rb = 0; rb < nrows; rb += U * R) {
+        uint4 w[U * R][CPT];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            uint4 w[CPT];
+        for (int r = 0; r < U * R; r++)
 #pragma unroll
             for (int c = 0; c < CPT; c++)
-                w[c] = (active && rb + r < nrows) ? ldg_stream16(wt + (size_t)(row0 + rb + r) * K + (size_t)c * NT * 8) : make_uint4(0u, 0u, 0u, 0u);
+                w[r][c] = (active && rb + r < nrows) ? ldg_stream16(wt + (size_t)(row0 + rb + r) * K + (size_t)c * NT * 8) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int m = 0; m < MB; m++) {
-                float a = 0.f;
+        for (int u = 0; u < U; u++) {
+            if (rb + u * R >= nrows) break;
+            float acc[16];
 #pragma unroll
-                for (int c = 0; c < CPT; c++) a = dot8(w[c], &xr[m][c * 8], a);
-                acc[r * MB + m] = a;
-            }
-        }
-        const float tot = warp_transpose_reduce<16>(acc, lane);
-        if (!(lane & 1)) red[buf][warp][lane >> 1] = tot;
-        __syncthreads();
-        if (warp == 0) {
-            float v = 0.f;
-            if (lane < 16) {
+            for (int r = 0; r < R; r++)
 #pragma unroll
-                for (int wv = 0; wv < DW; wv++) v += red[buf][wv][lane];
-            }
-            const int r = lane / MB, m = lane % MB, row = row0 + rb + r;
-            const float other = __shfl_xor_sync(0xffffffffu, v, MB);       /* row ^ 1, same m: the (gate, up) partner */
-            if (lane < 16 && rb + r < nrows && m < M) {
-                if (EPI == VB_EPI_SWIGLU) {
-                    if (!(row & 1)) C[(size_t)m * ldc + (row >> 1)] = vb_silu(v) * other;
-                } else {
-                    if (bias) v += bias[row];
-                    if (EPI == VB_EPI_GELU) v = vb_gelu_tanh(v);
-                    if (EPI == VB_EPI_RESIDUAL) v += C[(size_t)m * ldc + row];
-                    C[(size_t)m * ldc + row] = v;
+                for (int m = 0; m < MB; m++) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int c = 0; c < CPT; c++) a = dot8(w[u * R + r][c], &xr[m][c * 8], a);
+                    acc[r * MB + m] = a;
+                }
+            const float tot = warp_transpose_reduce<16>(acc, lane);
+            if (!(lane & 1)) red[buf][warp][lane >> 1] = tot;
+            __syncthreads();
+            if (warp == 0) {
+                float v = 0.f;
+                if (lane < 16) {
+#pragma unroll
+                    for (int wv = 0; wv < DW; wv++) v += red[buf][wv][lane];
+                }
+                const int r = lane / MB, m = lane % MB, row = row0 + rb + u * R + r;
+                const float other = __shfl_xor_sync(0xffffffffu, v, MB);       /* row ^ 1, same m: the (gate, up) partner */
+                if (lane < 16 && rb + u * R + r < nrows && m < M) {
+                    if (EPI == VB_EPI_SWIGLU) {
+                        if (!(row & 1)) C[(size_t)m * ldc + (row >> 1)] = vb_silu(v) * other;
+                    } else {
+                        if (bias) v += bias[row];
+                        if (EPI == VB_EPI_GELU) v = vb_gelu_tanh(v);
+                        if (EPI == VB_EPI_RESIDUAL) v += C[(size_t)m * ldc + row];
+                        C[(size_t)m * ldc + row] = v;
+                    }
                 }
             }
+            buf ^= 1;
         }
-        buf ^= 1;
     }
 }
 
