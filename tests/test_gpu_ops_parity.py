@@ -157,6 +157,9 @@ def test_softmax(vb, ref):
     (150, 900, 32, 32, 64, 750, 750),       # several 64-query tiles, ragged last tile, window start inside a key tile
     (70, 70, 32, 32, 64, 750, 0),           # stream start: keys < window
     (9, 9, 4, 2, 32, 3, 0),                 # tiny window
+    (5, 1755, 32, 32, 64, 750, 1750),       # live feed: 5 new positions against a full window (split-key kernel)
+    (3, 70, 32, 32, 64, 750, 67),           # split-key kernel with fewer keys than 8 warps x 4 for some warps
+    (2, 64, 32, 32, 64, 750, 10),           # split-key kernel, causal end before the end of the keys
 ])
 def test_causal_attention(vb, ref, seq_q, seq_k, H, Hkv, hd, win, qoff):
     rng = np.random.default_rng(7 + seq_q)

@@ -277,11 +277,15 @@ k_gemv_generic(float *__restrict__ y, const float *__restrict__ x, const uint16_
 template <int CPT, int MB, int EPI>
 __global__ void __launch_bounds__(DT, 1)
 k_gemv_cols(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda, const uint16_t *__restrict__ W,
-            const float *__restrict__ bias, int K, int N, int NT, int M) {
+            const float *__restrict__ bias, int K, int N, int NT, int M, int WG, int NG) {
     constexpr int R = 16 / MB;                                    /* rows per batch */
     __shared__ float red[2][DW][16];
+    /* A row of K <= 2048 occupies only NT = K/8 threads; the CTA then runs NG groups of WG warps, each group on its own
+     * batches of rows (K = 1280: 3 groups of 5 warps instead of 5 busy warps out of 16).  All groups step together, so one
+     * __syncthreads per batch serves them all. */
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const bool active = t < NT;
+    const int g = warp / WG, tl = t - g * WG * 32;
+    const bool active = g < NG && tl < NT;
     float xr[MB][CPT * 8];
 #pragma unroll
     for (int m = 0; m < MB; m++)
@@ -289,7 +293,7 @@ k_gemv_cols(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda
         for (int c = 0; c < CPT; c++) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
             if (active && m < M) {
-                const float4 *p = reinterpret_cast<const float4 *>(A + (size_t)m * lda + (size_t)(c * NT + t) * 8);
+                const float4 *p = reinterpret_cast<const float4 *>(A + (size_t)m * lda + (size_t)(c * NT + tl) * 8);
                 a = p[0]; b = p[1];
             }
             xr[m][c * 8 + 0] = a.x; xr[m][c * 8 + 1] = a.y; xr[m][c * 8 + 2] = a.z; xr[m][c * 8 + 3] = a.w;
@@ -297,12 +301,13 @@ k_gemv_cols(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda
         }
     int u0, nu; cta_rows(N / 2, u0, nu);                          /* row pairs: SwiGLU keeps (gate, up) in one CTA */
     const int row0 = u0 * 2, nrows = nu * 2;
-    const uint16_t *wt = W + (size_t)t * 8;
+    const uint16_t *wt = W + (size_t)(active ? tl : 0) * 8;
     /* U batches of R rows are loaded up front (8 rows = 128 bytes per thread in flight for CPT = 1: with MB = 8 a single batch would
      * be 2 rows and the kernel latency-bound), then reduced one after the other */
     constexpr int U = CPT == 1 ? (8 / R > 0 ? 8 / R : 1) : 1;
     int buf = 0;
-    for (int rb = 0; rb < nrows; rb += U * R) {
+    for (int base = 0; base < nrows; base += NG * U * R) {
+        const int rb = base + g * U * R;                          /* this group's rows (may lie past the end: masked) */
         uint4 w[U * R][CPT];
 #pragma unroll
         for (int r = 0; r < U * R; r++)
@@ -311,7 +316,7 @@ k_gemv_cols(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda
                 w[r][c] = (active && rb + r < nrows) ? ldg_stream16(wt + (size_t)(row0 + rb + r) * K + (size_t)c * NT * 8) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (rb + u * R >= nrows) break;
+            if (base + u * R >= nrows) break;                     /* uniform over the CTA: group 0 has the lowest rows */
             float acc[16];
 #pragma unroll
             for (int r = 0; r < R; r++)
@@ -325,12 +330,10 @@ k_gemv_cols(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda
             const float tot = warp_transpose_reduce<16>(acc, lane);
             if (!(lane & 1)) red[buf][warp][lane >> 1] = tot;
             __syncthreads();
-            if (warp == 0) {
+            if (g < NG && warp == g * WG) {
                 float v = 0.f;
-                if (lane < 16) {
-#pragma unroll
-                    for (int wv = 0; wv < DW; wv++) v += red[buf][wv][lane];
-                }
+                if (lane < 16)
+                    for (int wv = 0; wv < WG; wv++) v += red[buf][g * WG + wv][lane];
                 const int r = lane / MB, m = lane % MB, row = row0 + rb + u * R + r;
                 const float other = __shfl_xor_sync(0xffffffffu, v, MB);       /* row ^ 1, same m: the (gate, up) partner */
                 if (lane < 16 && rb + u * R + r < nrows && m < M) {
@@ -353,11 +356,12 @@ template <int CPT, int MB>
 static void gemv_cols_launch(VbEngine *e, float *C, int ldc, const float *A, int lda, const uint16_t *W, const float *bias,
                              int K, int N, int NT, int M, int epi) {
     const int G = e->sm_count;
+    const int WG = (NT + 31) / 32, NG = DW / WG > 0 ? DW / WG : 1;
     switch (epi) {
-    case VB_EPI_STORE:    k_gemv_cols<CPT, MB, VB_EPI_STORE><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M); break;
-    case VB_EPI_GELU:     k_gemv_cols<CPT, MB, VB_EPI_GELU><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M); break;
-    case VB_EPI_RESIDUAL: k_gemv_cols<CPT, MB, VB_EPI_RESIDUAL><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M); break;
-    case VB_EPI_SWIGLU:   k_gemv_cols<CPT, MB, VB_EPI_SWIGLU><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M); break;
+    case VB_EPI_STORE:    k_gemv_cols<CPT, MB, VB_EPI_STORE><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M, WG, NG); break;
+    case VB_EPI_GELU:     k_gemv_cols<CPT, MB, VB_EPI_GELU><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M, WG, NG); break;
+    case VB_EPI_RESIDUAL: k_gemv_cols<CPT, MB, VB_EPI_RESIDUAL><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M, WG, NG); break;
+    case VB_EPI_SWIGLU:   k_gemv_cols<CPT, MB, VB_EPI_SWIGLU><<<G, DT, 0, e->stream>>>(C, ldc, A, lda, W, bias, K, N, NT, M, WG, NG); break;
     }
 }
 

@@ -288,6 +288,85 @@ k_attn_warp(float *__restrict__ out, int ldo, const float *__restrict__ Q, int l
     for (int t = 0; t < EPL; t++) out[(size_t)i * ldo + h * hd + lane * EPL + t] = o[t] * inv;
 }
 
+/* Few queries against a long key range (the live stream's encoder calls: ~5 new positions x a 750-key window, where one warp
+ * per (query, head) is 160 warps walking 750 keys one after the other: 157 us per layer, profiles/r02_live.md).  One CTA per
+ * (query, head); its 8 warps take interleaved blocks of 4 keys (4 K/V rows in flight per warp, one softmax rescale per block),
+ * then the 8 partial (max, sum, o[]) states are merged.  Same masking and f32 arithmetic as k_attn_warp; the summation
+ * order differs (per-warp partial sums), i.e. results agree to f32 rounding, like the tiled kernel's. */
+template <int EPL>
+__global__ void __launch_bounds__(256)
+k_attn_split(float *__restrict__ out, int ldo, const float *__restrict__ Q, int ldq,
+             const float *__restrict__ K, const float *__restrict__ V, int ldkv,
+             int seq_q, int seq_k, int n_heads, int n_kv_heads, float scale, int window, int q_offset) {
+    constexpr int hd = EPL * 32;
+    __shared__ float s_m[8], s_l[8], s_o[8][hd];
+    const int i = blockIdx.x / n_heads, h = blockIdx.x % n_heads;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kvh = h / (n_heads / n_kv_heads);
+    const int g = q_offset + i;
+    int k_start = 0;
+    if (window > 0 && g - window + 1 > 0) k_start = g - window + 1;
+    int k_end = g + 1;
+    if (k_end > seq_k) k_end = seq_k;
+
+    float q[EPL], o[EPL];
+#pragma unroll
+    for (int t = 0; t < EPL; t++) { q[t] = Q[(size_t)i * ldq + h * hd + lane * EPL + t]; o[t] = 0.f; }
+    float mx = -1e30f, sum = 0.f;
+    const size_t col = (size_t)kvh * hd + lane * EPL;
+    for (int j0 = k_start + warp * 4; j0 < k_end; j0 += 32) {
+        float kk[4][EPL], vv[4][EPL], s[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const bool ok = j0 + jj < k_end;
+            const size_t off = (size_t)(ok ? j0 + jj : j0) * ldkv + col;
+#pragma unroll
+            for (int t = 0; t < EPL; t++) { kk[jj][t] = K[off + t]; vv[jj][t] = V[off + t]; }
+        }
+        float mb = -1e30f;
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            float d = 0.f;
+#pragma unroll
+            for (int t = 0; t < EPL; t++) d = fmaf(q[t], kk[jj][t], d);
+            d = vb_warp_sum(d) * scale;
+            s[jj] = j0 + jj < k_end ? d : -1e30f;
+            mb = fmaxf(mb, s[jj]);
+        }
+        if (mb > mx) {
+            const float c = expf(mx - mb);
+            sum *= c;
+#pragma unroll
+            for (int t = 0; t < EPL; t++) o[t] *= c;
+            mx = mb;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const float p = s[jj] > -1e29f ? expf(s[jj] - mx) : 0.f;
+            sum += p;
+#pragma unroll
+            for (int t = 0; t < EPL; t++) o[t] = fmaf(p, vv[jj][t], o[t]);
+        }
+    }
+    if (lane == 0) { s_m[warp] = mx; s_l[warp] = sum; }
+#pragma unroll
+    for (int t = 0; t < EPL; t++) s_o[warp][lane * EPL + t] = o[t];
+    __syncthreads();
+    for (int d = threadIdx.x; d < hd; d += 256) {
+        float M = -1e30f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) M = fmaxf(M, s_m[w]);
+        float L = 0.f, acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const float c = s_l[w] > 0.f ? expf(s_m[w] - M) : 0.f;
+            L = fmaf(s_l[w], c, L);
+            acc = fmaf(s_o[w][d], c, acc);
+        }
+        out[(size_t)i * ldo + h * hd + d] = L > 0.f ? acc / L : 0.f;
+    }
+}
+
 /* Tiled flash attention for the encoder shape (head_dim 64, MHA): one CTA = 64 queries of one head, K/V streamed in
  * 64-key tiles through shared memory, S = QK^T and O += PV as 4x4 register blocks, online softmax per row.
  * Same masking as k_attn_warp (keys [max(0,g-W+1), min(g,seq_k-1)], g = q_offset+i); exact f32 arithmetic. */
@@ -432,18 +511,28 @@ void vb_attention_rows(VbEngine *e, float *out, int ldo, const float *Q, int ldq
         vb_launch_count(e, 1);
         return;
     }
+    if (seq_q < 16 && seq_k >= 64 && (long long)seq_q * n_heads <= 65535) {
+        const int blocks = seq_q * n_heads;
+#define ATT_SPLIT(E) case E: k_attn_split<E><<<blocks, 256, 0, e->stream>>>(out, ldo, Q, ldq, K, V, ldkv, seq_q, seq_k, \
+                         n_heads, n_kv_heads, scale, window, q_offset); break;
+        switch (head_dim % 32 ? 0 : head_dim / 32) {
+            ATT_SPLIT(1) ATT_SPLIT(2) ATT_SPLIT(3) ATT_SPLIT(4) ATT_SPLIT(8)
+        default: VB_FAIL("attention head_dim unsupported (need 32,64,96,128,256)");
+        }
+#undef ATT_SPLIT
+        VB_CUDA_OK(cudaGetLastError());
+        vb_launch_count(e, 1);
+        return;
+    }
     long long warps = (long long)seq_q * n_heads;
     int blocks = (int)((warps * 32 + 255) / 256);
 #define ATT_CASE(E) case E: k_attn_warp<E><<<blocks, 256, 0, e->stream>>>(out, ldo, Q, ldq, K, V, ldkv, seq_q, seq_k, \
                          n_heads, n_kv_heads, scale, window, q_offset); break;
-    switch (head_dim / 32) {
+    switch (head_dim % 32 ? 0 : head_dim / 32) {
         ATT_CASE(1) ATT_CASE(2) ATT_CASE(3) ATT_CASE(4) ATT_CASE(8)
-    default:
-        fprintf(stderr, "voxtral_b200: attention head_dim %d unsupported (need 32,64,96,128,256)\n", head_dim);
-        abort();
+    default: VB_FAIL("attention head_dim unsupported (need 32,64,96,128,256)");
     }
 #undef ATT_CASE
-    if (head_dim % 32) { fprintf(stderr, "voxtral_b200: attention head_dim %d not a multiple of 32\n", head_dim); abort(); }
     VB_CUDA_OK(cudaGetLastError());
     vb_launch_count(e, 1);
 }
