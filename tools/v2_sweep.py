@@ -18,7 +18,7 @@ pcm = read_wav_f32(synth_wav(seconds))
 eng = vb.Engine(ensure_synth_model())
 forks = []
 h = lambda ids: hashlib.md5(ids.tobytes()).hexdigest()[:10]
-KEYS = ("VOX_CUDA_V2_INFLIGHT", "VOX_CUDA_V2_DYNAMIC", "VOX_CUDA_V2_PROF", "VOX_CUDA_V2_DBG")
+KEYS = ("VOX_CUDA_V2_INFLIGHT", "VOX_CUDA_V2_DYNAMIC", "VOX_CUDA_V2_PROF", "VOX_CUDA_V2_DBG", "VOX_CUDA_V2_LL")
 for cfg in configs:
     parts = cfg.split(":")
     mode, n = parts[0], int(parts[1]) if len(parts) > 1 and parts[1] else 1

@@ -84,6 +84,7 @@ struct V2Smem {
     int v_pos, v_token, v_arow, v_left, v_nout, v_eos, v_passes;
     int dr_key[V2_DRAFT_TAB], dr_succ[V2_DRAFT_TAB];
     volatile int abort_flag, is_last;
+    long long prof_t, prof_acc[16]; int prof_cnt[8];   /* profiled step: cycles before / inside v2_consume and chunks per sub-phase kind */
 };
 
 __device__ __forceinline__ bool mbar_test_wait(uint64_t *b, uint32_t parity) {
@@ -675,6 +676,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
     if (tid == 0) {
         for (int i = 0; i < V2_SLOTS; i++) { mbar_init(&sm->full[i], 1); mbar_init(&sm->empty[i], V2_CW); }
         sm->abort_flag = 0; sm->is_last = 0;
+        for (int i = 0; i < 16; i++) sm->prof_acc[i] = 0;
+        for (int i = 0; i < 8; i++) sm->prof_cnt[i] = 0;
         for (int b = 0; b < V2_MAXB; b++) {
             const bool on = b < a.nb && a.col[b].n_steps > 0;
             sm->c_pos[b] = a.col[b].pos0; sm->c_token[b] = a.col[b].token0; sm->c_arow[b] = a.col[b].arow0;
@@ -732,6 +735,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
             const int layer = idx / 7;
             const int sub = layer == VOX_DEC_LAYERS ? 7 : idx - layer * 7;
             if (sub == 0 || sub == 7) V2PROF();
+            const bool pstep = a.prof && step == a.prof_step && tid == 0 && layer >= 1 && layer < VOX_DEC_LAYERS - 1;
+            if (pstep) sm->prof_t = clock64();
             /* ---- this phase's activation columns: 8 values x NB per thread ---- */
             V2X<NB> x;
             int seg_bytes = VOX_DEC_DIM * 2, NT = V2_CONS;
@@ -752,6 +757,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                 v2_rmsnorm<NB>(x, nw, sub == 3 ? p.ada + (size_t)layer * VOX_DEC_DIM : nullptr, sm);
             }
             const float *inv_freq = p.inv_freq;
+            if (pstep) { const long long tn = clock64(); sm->prof_acc[sub] += tn - sm->prof_t; sm->prof_t = tn; sm->prof_cnt[sub] -= (int)it + 1; }
             v2_consume<NB>(sm, slots, it, seg_bytes, NT, x, redbuf, grp, err, tacc, timing, a.dbg, [&](int row, int b, float v, int, bool valid) {
                 const float other = __shfl_xor_sync(0xffffffffu, v, NB);    /* row ^ 1 of the same column: RoPE pair / (gate, up) pair */
                 if (!valid) return;
@@ -782,6 +788,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
                     break; }
                 }
             });
+            if (pstep) { sm->prof_acc[8 + sub] += clock64() - sm->prof_t; sm->prof_cnt[sub] += (int)it; }
             if (sub == 0) {
                 V2PROF();
                 v2_grid_barrier(a.bar, gen, err);
@@ -871,6 +878,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_dec_v2(const __grid_constant_
     if (a.prof && lane == 0 && (tid == 0 || tid == V2_CONS - 32)) {            /* warp 0 and the epilogue warp */
         long long *pp = a.prof + (size_t)blockIdx.x * V2_PROF_SLOTS + V2_PROF_SLOTS - (tid == 0 ? 20 : 14);
         for (int i = 0; i < 5; i++) pp[i] = tacc[i];
+        if (tid == 0) for (int i = 0; i < 16; i++) a.prof[(size_t)blockIdx.x * V2_PROF_SLOTS + 270 + i] = sm->prof_acc[i];
+        if (tid == 0) for (int i = 0; i < 8; i++) a.prof[(size_t)blockIdx.x * V2_PROF_SLOTS + 286 + i] = sm->prof_cnt[i];
     }
     if (tid == 0) {
         sm->abort_flag = 1;                                            /* the producer may be ahead of an early exit (EOS) */
@@ -967,6 +976,12 @@ static void v2_prof_report(VbEngine *e, const V2Args &a) {
         const long long *w0 = t + V2_PROF_SLOTS - 20, *w11 = t + V2_PROF_SLOTS - 14;
         fprintf(stderr, "[v2 prof nb=%d] cta %3d consumer cycles per chunk  warp 0: wait-data %.0f math %.0f reduce %.0f cta-barrier %.0f | epilogue warp: wait-data %.0f math %.0f reduce %.0f cta-barrier %.0f epilogue %.0f\n",
                 a.nb, ctas[ci], w0[0] / nc, w0[1] / nc, w0[2] / nc, w0[3] / nc, w11[0] / nc, w11[1] / nc, w11[2] / nc, w11[3] / nc, w11[4] / nc);
+        /* sub-phases 0 QKV | 1,2 wo blocks | 3 w1|w3 | 4,5,6 w2 blocks: cycles of thread 0 from the top of the sub-phase to the first
+         * chunk (activation load, RMSNorm; the load's latency itself overlaps the first chunk) | inside the weight loop / chunks taken */
+        const long long *sa = t + 270;
+        fprintf(stderr, "[v2 prof nb=%d] cta %3d sub-phase cycles per layer (activation load + norm | weight loop / chunks):", a.nb, ctas[ci]);
+        for (int k = 0; k < 7; k++) fprintf(stderr, " s%d=%.0f|%.0f/%.1f", k, sa[k] / (double)(VOX_DEC_LAYERS - 2), sa[8 + k] / (double)(VOX_DEC_LAYERS - 2), sa[16 + k] / (double)(VOX_DEC_LAYERS - 2));
+        fprintf(stderr, "\n");
     }
     free(h);
 }
