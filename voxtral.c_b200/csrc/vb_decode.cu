@@ -487,10 +487,10 @@ static int decode_driver(VbEngine *e) {
     }
     if (e->decode_mode != 1 && e->decode_mode != 3 && e->decode_mode != 5) e->decode_mode = vb_decoder_v2_supported(e) ? 5 : vb_decoder_persist_supported(e) ? 3 : 1;
     if (e->decode_mode == 3 && !vb_decoder_persist_supported(e)) {
-        fprintf(stderr, "voxtral_b200: persistent decode kernel requested but cooperative launch is unavailable\n"); abort();
+        VB_FAIL("persistent decode kernel requested but cooperative launch is unavailable");
     }
     if (e->decode_mode == 5 && !vb_decoder_v2_supported(e)) {
-        fprintf(stderr, "voxtral_b200: v2 decode kernel requested but unavailable on this device\n"); abort();
+        VB_FAIL("v2 decode kernel requested but unavailable on this device");
     }
     return e->decode_mode;
 }
@@ -576,7 +576,7 @@ extern "C" int vb_decoder_step_from_embed(VbEngine *e, const float *d_embed, int
 extern "C" void vb_gemv_bf16_dev(VbEngine *e, float *y, const float *x, const uint16_t *W, const float *bias, int K, int N) {
     int chunks = K / 8, cpt = 1;
     while (cpt <= 4 && (chunks % cpt || chunks / cpt > DT)) cpt++;
-    if (K % 8 || cpt > 4) { fprintf(stderr, "voxtral_b200: GEMV K=%d unsupported\n", K); abort(); }
+    if (K % 8 || cpt > 4) { fprintf(stderr, "voxtral_b200: GEMV K=%d unsupported\n", K); VB_FAIL("GEMV shape unsupported"); }
     int NT = chunks / cpt, G = e->sm_count;
     switch (cpt) {
     case 1: k_gemv_generic<1><<<G, DT, 0, e->stream>>>(y, x, W, bias, K, N, NT); break;
@@ -594,8 +594,10 @@ extern "C" void vb_decoder_prefill_dev(VbEngine *e, const float *d_embeds, int n
     if (n <= 0) return;
     vb_decoder_alloc(e);
     if (start_pos + n > VB_KV_SLOTS) {
+        /* the M > 1 attention addresses keys by physical row: a prompt may not cross the end of the ring (the stream API
+         * prefills at position 0 only; 8192 slots).  An error for the caller's guard, not a process abort. */
         fprintf(stderr, "voxtral_b200: prefill of %d tokens at position %d would wrap the KV ring\n", n, start_pos);
-        abort();
+        VB_FAIL("prefill would wrap the KV ring");
     }
     float *x = vb_ws(e, 0, (size_t)n * DEC_DIM * 4);
     float *xn = vb_ws(e, 1, (size_t)n * DEC_DIM * 4);

@@ -225,13 +225,13 @@ __global__ void __launch_bounds__(MK_CONS, 1) k_dec_persist(MegaArgs a) {
 }
 
 extern "C" int vb_decoder_persist_supported(VbEngine *e) {
-    static int cached = -1;
-    if (cached >= 0) return cached;
+    if (e->persist_checked) return e->persist_ok;                   /* per engine = per device */
+    e->persist_checked = 1; e->persist_ok = 0;
     int coop = 0, blocks = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
-    if (!coop || e->sm_count > 160) { cached = 0; return 0; }       /* attention merge assumes <= 20 CTAs per kv head */
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_dec_persist, MK_CONS, 0) != cudaSuccess || blocks < 1) { cached = 0; return 0; }
-    cached = 1;
+    if (!coop || e->sm_count > 160) return 0;                       /* attention merge assumes <= 20 CTAs per kv head */
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_dec_persist, MK_CONS, 0) != cudaSuccess || blocks < 1) return 0;
+    e->persist_ok = 1;
     return 1;
 }
 

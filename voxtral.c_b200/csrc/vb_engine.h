@@ -142,6 +142,7 @@ typedef struct VbEngine {
     cudaGraphExec_t step_graph;                 /* one decode step, device-state driven */
     int step_graph_ready;
     VbV2Scratch v2; int v2_checked, v2_ok;
+    int persist_checked, persist_ok;            /* vb_decoder_persist_supported, cached per engine */
     int verify_depth;                           /* > 1: exact multi-token decoding with that many positions per weight pass (vb_decode_v2.cu) */
     long long verify_passes, verify_tokens;     /* weight passes spent / tokens emitted in verify mode */
     const uint8_t *pin_base; size_t pin_bytes;  /* vox_load: the mmap'd checkpoint while it is registered as pinned memory (async H2D) */

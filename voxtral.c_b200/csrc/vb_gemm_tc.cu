@@ -239,8 +239,7 @@ static void make_map(CUtensorMap *map, const void *base, uint64_t inner_elems, u
         cudaDriverEntryPointQueryResult q;
         void *fn = NULL;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
-            fprintf(stderr, "voxtral_b200: cuTensorMapEncodeTiled unavailable (driver too old for TMA)\n");
-            abort();
+            VB_FAIL("cuTensorMapEncodeTiled unavailable (driver too old for TMA)");
         }
         g_encode = (PFN_encodeTiled)fn;
     }
@@ -249,7 +248,7 @@ static void make_map(CUtensorMap *map, const void *base, uint64_t inner_elems, u
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { fprintf(stderr, "voxtral_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r); abort(); }
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "voxtral_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r); VB_FAIL("cuTensorMapEncodeTiled failed"); }
 }
 
 int vb_gemm_tc_usable(int M, int N, int K) {
@@ -264,7 +263,8 @@ int vb_gemm_nsplit(void) {
 
 void vb_gemm_tc(VbEngine *e, const float *A, int lda, const uint16_t *W, const float *bias, float *C, int ldc,
                 int M, int N, int K, int epi) {
-    static int attr_done = 0;
+    static unsigned int attr_done = 0;                              /* one bit per device: function attributes are per device */
+    const unsigned int dev_bit = 1u << (e->device & 31);
     const int nsplit = vb_gemm_nsplit();
     uint16_t *planes = (uint16_t *)vb_ws(e, VB_WS_GEMM_PLANES, (size_t)nsplit * M * K * 2 + 256);
     long long quads = ((long long)M * K + 3) / 4;
@@ -272,12 +272,12 @@ void vb_gemm_tc(VbEngine *e, const float *A, int lda, const uint16_t *W, const f
     CUtensorMap tmA, tmW;
     make_map(&tmA, planes, (uint64_t)K, (uint64_t)nsplit * M, (uint64_t)K * 2);
     make_map(&tmW, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2);
-    if (!attr_done) {
+    if (!(attr_done & dev_bit)) {
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<VB_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<VB_EPI_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<VB_EPI_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<VB_EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr_done = 1;
+        attr_done |= dev_bit;
     }
     dim3 grid(N / TC_BN, (M + TC_BM - 1) / TC_BM), block(TC_THREADS);
     switch (epi) {

@@ -70,6 +70,7 @@ static void build_filters(float *filt /* [N_MEL][N_FREQ] */) {
 
 static const MelTables *mel_tables(int device) {
     for (int i = 0; i < g_tab_n; i++) if (g_tab[i].device == device) return &g_tab[i];
+    if (g_tab_n >= (int)(sizeof g_tab / sizeof g_tab[0])) VB_FAIL("mel tables: more than 16 devices in one process");
     float *cosT = (float *)calloc((size_t)N_FFT * KPAD, 4), *sinT = (float *)calloc((size_t)N_FFT * KPAD, 4);
     float *filt = (float *)malloc((size_t)N_MEL * N_FREQ * 4), *filtT = (float *)calloc((size_t)N_FREQ * N_MEL, 4);
     float win[N_FFT];

@@ -502,9 +502,10 @@ void vb_attention_rows(VbEngine *e, float *out, int ldo, const float *Q, int ldq
                        int head_dim, float scale, int window, int q_offset) {
     if (seq_q <= 0) return;
     if (head_dim == AT_HD && n_heads == n_kv_heads && seq_q >= 16 && (ldq % 4) == 0 && (ldkv % 4) == 0 && (ldo % 4) == 0) {
-        static int attr_done = 0;
+        static unsigned int attr_done = 0;                          /* one bit per device */
+        const unsigned int dev_bit = 1u << (e->device & 31);
         const int smem = 4 * AT_HD * AT_LD * (int)sizeof(float);
-        if (!attr_done) { VB_CUDA_OK(cudaFuncSetAttribute(k_attn_tile64, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_done = 1; }
+        if (!(attr_done & dev_bit)) { VB_CUDA_OK(cudaFuncSetAttribute(k_attn_tile64, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_done |= dev_bit; }
         dim3 grid((seq_q + AT_BQ - 1) / AT_BQ, n_heads);
         k_attn_tile64<<<grid, 256, smem, e->stream>>>(out, ldo, Q, ldq, K, V, ldkv, seq_q, seq_k, scale, window, q_offset);
         VB_CUDA_OK(cudaGetLastError());
