@@ -160,6 +160,11 @@ def test_softmax(vb, ref):
     (5, 1755, 32, 32, 64, 750, 1750),       # live feed: 5 new positions against a full window (split-key kernel)
     (3, 70, 32, 32, 64, 750, 67),           # split-key kernel with fewer keys than 8 warps x 4 for some warps
     (2, 64, 32, 32, 64, 750, 10),           # split-key kernel, causal end before the end of the keys
+    (300, 1500, 32, 32, 64, 750, 1200),     # tcgen05 kernel: three 128-query tiles, 14 key blocks each, full window, ragged last tile
+    (128, 128, 32, 32, 64, 750, 0),         # tcgen05 kernel: exactly one tile, two key blocks, pure causal mask
+    (129, 1000, 32, 32, 64, 750, 871),      # tcgen05 kernel: a second tile with a single row
+    (33, 97, 32, 32, 64, 40, 64),           # tcgen05 kernel: small window that starts and ends inside key blocks
+    (200, 200, 4, 4, 64, 100, 0),           # tcgen05 kernel: 4 heads, window shorter than the tile
 ])
 def test_causal_attention(vb, ref, seq_q, seq_k, H, Hkv, hd, win, qoff):
     rng = np.random.default_rng(7 + seq_q)

@@ -37,6 +37,9 @@
 #define VB_WS_ALT    20   /* 8 floats: result of the alternatives kernel (vb_decode.cu) */
 #define VB_WS_DIST_X 21   /* 21-23: sharded encoder (vb_dist.c): own rows, K and V with halo */
 #define VB_WS_GEMM_PLANES 24  /* bf16 split planes of the tcgen05 GEMM (vb_gemm_tc.cu) */
+#define VB_WS_ATT_QP 25      /* 25-27: bf16 planes of Q, K and V^T for the tcgen05 attention (vb_attn_tc.cu) */
+#define VB_WS_ATT_KP 26
+#define VB_WS_ATT_VT 27
 
 /* Error boundary.  Inside the library a failed CUDA call (cudaMalloc out of memory, a launch error...) reports through
  * vb_cuda_fail().  Public entry points that have an error return in the reference -- vox_load -> NULL (voxtral.c:132-158),

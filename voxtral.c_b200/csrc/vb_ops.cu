@@ -501,6 +501,10 @@ void vb_attention_rows(VbEngine *e, float *out, int ldo, const float *Q, int ldq
                        const float *V, int ldkv, int seq_q, int seq_k, int n_heads, int n_kv_heads,
                        int head_dim, float scale, int window, int q_offset) {
     if (seq_q <= 0) return;
+    if (vb_attn_tc_enabled() && vb_attn_tc_usable(seq_q, seq_k, n_heads, n_kv_heads, head_dim, ldq, ldkv, ldo)) {
+        vb_attention_tc(e, out, ldo, Q, ldq, K, V, ldkv, seq_q, seq_k, n_heads, scale, window, q_offset);
+        return;
+    }
     if (head_dim == AT_HD && n_heads == n_kv_heads && seq_q >= 16 && (ldq % 4) == 0 && (ldkv % 4) == 0 && (ldo % 4) == 0) {
         static unsigned int attr_done = 0;                          /* one bit per device */
         const unsigned int dev_bit = 1u << (e->device & 31);

@@ -30,6 +30,12 @@ void vb_attention_rows(VbEngine *e, float *out, int ldo, const float *Q, int ldq
                        const float *V, int ldkv, int seq_q, int seq_k, int n_heads, int n_kv_heads,
                        int head_dim, float scale, int window, int q_offset);
 
+/* vb_attn_tc.cu: the same attention on tcgen05 (head_dim 64, MHA, >= 32 queries) */
+int  vb_attn_tc_enabled(void);
+int  vb_attn_tc_usable(int seq_q, int seq_k, int n_heads, int n_kv_heads, int head_dim, int ldq, int ldkv, int ldo);
+void vb_attention_tc(VbEngine *e, float *out, int ldo, const float *Q, int ldq, const float *K, const float *V, int ldkv,
+                     int seq_q, int seq_k, int n_heads, float scale, int window, int q_offset);
+
 void vb_launch_count(VbEngine *e, int n);
 
 /* ---- device helpers ---- */
