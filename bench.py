@@ -96,6 +96,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 0.0))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1500.0, "fallback (B200_PROFILING.md)"
+
+
+# f32-equivalent flops per encoder position: 32 layers x (wq|wk|wv + wo + w1|w3 + w2) = 1.93 GFLOP of linears
+# + 0.197 GFLOP of window-750 attention.  The tensor cores execute 3 bf16 plane products per linear MAC and 6 per attention MAC.
+ENC_LINEAR_GFLOP, ENC_ATTN_GFLOP = 1.93, 0.197
+
+
+def encoder_block(positions_per_s):
+    peak, src = tensor_peak()
+    useful = (ENC_LINEAR_GFLOP + ENC_ATTN_GFLOP) * positions_per_s / 1e3
+    issued = (3 * ENC_LINEAR_GFLOP + 6 * ENC_ATTN_GFLOP) * positions_per_s / 1e3
+    return {"positions_per_s": positions_per_s, "bound": "tensor", "useful_tflops_f32_equivalent": useful,
+            "issued_bf16_tflops": issued, "peak": peak, "unit": "TFLOP/s", "frac_issued": issued / peak if peak else None,
+            "peak_source": src,
+            "note": "whole encoder pass (mel, conv stem, 32 layers, adapter) timed with CUDA events; issued = 3 bf16 plane products "
+                    "per linear MAC (exact f32 activations x bf16 weights) and 6 per attention MAC (f32 x f32), all on tcgen05"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -402,6 +426,8 @@ def main():
             "decode_ms_per_step": step_ms,
             "encoder_positions_per_s": ((i_after["total_encoder_positions"] - i_before["total_encoder_positions"]) /
                                         max((i_after["total_encoder_ms"] - i_before["total_encoder_ms"]) / 1e3, 1e-9)),
+            "encoder": encoder_block((i_after["total_encoder_positions"] - i_before["total_encoder_positions"]) /
+                                     max((i_after["total_encoder_ms"] - i_before["total_encoder_ms"]) / 1e3, 1e-9)),
             "load_s": load_s, "load_s_library": eng.info()["load_ms"] / 1e3,
             "gpu_launches": int(i_after["kernel_launches"] - i_before["kernel_launches"]),
             "clocks": sampler.summary(),
