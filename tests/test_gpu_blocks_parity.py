@@ -100,3 +100,45 @@ def test_encoder_forward_full(engine, ref, refctx, vb, frames):
     # its row scale (tests/test_gpu_ops_parity.py::test_linear_bf16) and the layer stack amplifies what the conv stem introduces;
     # measured 6e-5 of the output scale on a B200 (the incremental test above, which starts after the conv stem, sees 1e-5).
     assert err <= 1.5e-4 * max(scale, 1.0)
+
+
+def test_encoder_forward_long_call_fused_equals_unfused(engine, ref, refctx, vb):
+    """A call long enough (550 positions >= 512) for the persistent tcgen05 GEMM, the tcgen05 attention over several query tiles
+    and the fused producers (RMSNorm / attention / SwiGLU writing bf16 planes): (1) within tolerance of the reference's
+    vox_encoder_forward, (2) bit-identical to the same call with the separate split passes (VOX_CUDA_FUSE=0)."""
+    import os
+    frames = 1100
+    rng = np.random.default_rng(71)
+    mel = (rng.normal(size=(frames, 128)) * 0.5).astype(np.float32)
+    L = vb.lib()
+    L.vox_encoder_forward.restype = fp
+    L.vox_encoder_forward.argtypes = [C.c_void_p, fp, C.c_int, C.POINTER(C.c_int)]
+
+    def run():
+        n = C.c_int()
+        p = L.vox_encoder_forward(engine.ctx, P(mel), frames, C.byref(n))
+        out = np.ctypeslib.as_array(p, shape=(n.value * 1280,)).copy().reshape(n.value, 1280)
+        L.free_(C.cast(p, C.c_void_p))
+        return out
+
+    a = run()
+    for var in ("VOX_CUDA_FUSE_QKV", "VOX_CUDA_FUSE"):      # without the wq|wk|wv epilogue fusion; without any fused producer
+        old = os.environ.get(var)
+        os.environ[var] = "0"
+        try:
+            a0 = run()
+        finally:
+            if old is None:
+                del os.environ[var]
+            else:
+                os.environ[var] = old
+        assert np.array_equal(a, a0), f"encoder output with {var}=0 differs from the fused path: max {np.abs(a - a0).max():.3e}"
+    nb = C.c_int()
+    pb = ref.L.vox_encoder_forward(refctx, P(mel.copy()), frames, C.byref(nb))
+    b = np.ctypeslib.as_array(pb, shape=(nb.value * 1280,)).copy().reshape(nb.value, 1280)
+    ref.free(C.cast(pb, C.c_void_p))
+    assert a.shape == b.shape == (550, 1280)
+    scale = float(np.abs(b).max())
+    err = float(np.abs(a - b).max())
+    print(f"vox_encoder_forward({frames} frames, persistent GEMM + tcgen05 attention): max abs diff {err:.2e} on a scale of {scale:.2f}")
+    assert err <= 1.5e-4 * max(scale, 1.0)

@@ -35,9 +35,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
 
 seconds = sys.argv[1] if len(sys.argv) > 1 else "60"
 passes = sys.argv[2] if len(sys.argv) > 2 else "3"
-for name, env in (("tcgen05 attention + persistent 128x256 GEMM", {}),
+only = set(sys.argv[3].split(",")) if len(sys.argv) > 3 else None      # e.g. 0,4: variant indices
+for idx, (name, env) in enumerate((("default: tcgen05 attention + persistent GEMM + fused producers (RoPE/planes as epilogues)", {}),
+                  ("... without the wq|wk|wv epilogue fusion", {"VOX_CUDA_FUSE_QKV": "0"}),
+                  ("... without any fused producer (separate k_split_planes passes)", {"VOX_CUDA_FUSE": "0"}),
                   ("tcgen05 attention + 128x128 GEMM (round 1)", {"VOX_CUDA_GEMM": "v1"}),
-                  ("CUDA-core attention + persistent GEMM", {"VOX_CUDA_ATTN": "simt"}),
-                  ("round-1 kernels", {"VOX_CUDA_ATTN": "simt", "VOX_CUDA_GEMM": "v1"})):
+                  ("round-1 kernels (CUDA-core attention, 128x128 GEMM)", {"VOX_CUDA_ATTN": "simt", "VOX_CUDA_GEMM": "v1"}))):
+    if only is not None and str(idx) not in only:
+        continue
     print(f"{name} ({seconds} s clip):", flush=True)
     subprocess.call([sys.executable, os.path.abspath(__file__), "--child", seconds, passes], env={**os.environ, **env})

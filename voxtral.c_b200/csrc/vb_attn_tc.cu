@@ -29,7 +29,7 @@
 #define FA_BQ 128
 #define FA_BK 64
 #define FA_HD 64
-#define FA_THREADS 192
+#define FA_THREADS 320                          /* TMA warp, MMA warp, 8 softmax warps */
 #define FA_QPLANE (FA_BQ * 128)                 /* 16 KB: 128 rows x 64 bf16 */
 #define FA_KTILE  (FA_BK * 128)                 /*  8 KB: 64 keys x 64 bf16 */
 #define FA_VTILE  (FA_HD * 128)                 /*  8 KB: 64 d rows x 64 keys */
@@ -40,13 +40,20 @@
 #define FA_OFF_V (FA_OFF_K + FA_K_SLOTS * 3 * FA_KTILE)
 #define FA_OFF_P (FA_OFF_V + FA_V_SLOTS * 3 * FA_VTILE)
 #define FA_OFF_BAR (FA_OFF_P + 3 * FA_QPLANE)
-#define FA_SMEM_BYTES (FA_OFF_BAR + 256 + 1024 /*align*/)
+#define FA_OFF_XCH (FA_OFF_BAR + 256)          /* 4 x 128 floats: partial row maxima, then 2 x 128: partial row sums */
+#define FA_SMEM_BYTES (FA_OFF_XCH + 6 * FA_BQ * 4 + 1024 /*align*/)
 #define FA_TMEM_COLS 256
 
 /* the six plane pairs (a plane, b plane), largest first: (0,0) (0,1) (1,0) (1,1) (0,2) (2,0) */
 #define FA_PA(pr) ((0x201100u >> (4 * (pr))) & 0xFu)
 #define FA_PB(pr) ((0x021010u >> (4 * (pr))) & 0xFu)
 
+/* e^x for x <= 0 through ex2.approx (relative error 2^-22; the argument product rounds at 2^-24 |x|) */
+__device__ __forceinline__ float fa_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 __device__ __forceinline__ void fa_sts128(uint32_t saddr, const uint32_t (&w)[4]) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
@@ -82,7 +89,8 @@ k_vt_planes(const float *__restrict__ V, int ldkv, int seq_k, int cols, int nk_p
 
 __global__ void __launch_bounds__(FA_THREADS, 1)
 k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-          float *__restrict__ out, int ldo, int seq_q, int seq_k, int cols, float scale, int window, int q_offset) {
+          float *__restrict__ out, int ldo, int seq_q, int seq_k, int cols, float scale, int window, int q_offset,
+          uint16_t *__restrict__ oplanes /* if set: the result as [3][seq_q][cols] bf16 planes (A operand of the wo GEMM) instead of out */) {
     extern __shared__ uint8_t fa_smem_raw[];
     uint8_t *sm = reinterpret_cast<uint8_t *>(((uintptr_t)fa_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + FA_OFF_BAR);
@@ -116,10 +124,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         for (int i = 0; i < FA_K_SLOTS; i++) { tc_mbar_init(&k_full[i], 1); tc_mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < 2; i++) {
             tc_mbar_init(&v_full[i], 1); tc_mbar_init(&v_empty[i], 1);
-            tc_mbar_init(&s_full[i], 1); tc_mbar_init(&s_empty[i], 128);
-            tc_mbar_init(&o_full[i], 1); tc_mbar_init(&o_empty[i], 128);
+            tc_mbar_init(&s_full[i], 1); tc_mbar_init(&s_empty[i], 256);
+            tc_mbar_init(&o_full[i], 1); tc_mbar_init(&o_empty[i], 256);
         }
-        tc_mbar_init(p_full, 128);
+        tc_mbar_init(p_full, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -195,52 +203,68 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             }
         }
     } else {
-        /* softmax warps 2..5: a warp may only touch TMEM lanes [32*(warp%4), +32) */
-        const int qd = warp & 3;
+        /* softmax warps 2..9: a warp may only touch TMEM lanes [32*(warp%4), +32); warps w and w+4 share the rows of a lane
+         * quarter and split the 64 columns (keys of S, head dims of O) in halves.  The only thing the halves exchange per key
+         * block is their partial row maximum (shared memory + one named barrier); their partial row sums meet at the end. */
+        const int qd = warp & 3, hf = (warp - 2) >> 2;
         const int r = qd * 32 + lane;                                   /* row of the query tile */
-        const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+        const uint32_t lane_off = ((uint32_t)(qd * 32) << 16) + (uint32_t)(hf * 32);
         const int g = q_offset + q0 + r;                                /* index of this query in the key buffer */
         int lo = 0;
         if (window > 0 && g - window + 1 > 0) lo = g - window + 1;
         const int hi = min(g, seq_k - 1);
-        float o[FA_HD];
+        /* key blocks every real row of the tile sees completely need no mask */
+        int lo_max = 0;
+        if (window > 0 && g_last - window + 1 > 0) lo_max = g_last - window + 1;
+        const int hi_min = min(g_first, seq_k - 1);
+        float o[32];
 #pragma unroll
-        for (int d = 0; d < FA_HD; d++) o[d] = 0.f;
+        for (int d = 0; d < 32; d++) o[d] = 0.f;
         float m = -1e30f, l = 0.f, alpha_prev = 1.f;
         const uint32_t prow = s32(sm + FA_OFF_P) + r * 128;
         const int sw = r & 7;
+        float *xch = reinterpret_cast<float *>(sm + FA_OFF_XCH);        /* [2 parities][2 halves][128 rows] */
 
         for (int j = 0; j < nb; j++) {
             const int b = j & 1;
-            const int c_lo = lo - (k_lo + j * FA_BK), c_hi = hi - (k_lo + j * FA_BK);
-            uint32_t s0[32], s1[32];
+            const int k0 = k_lo + j * FA_BK;
+            uint32_t sv[32];
             tc_mbar_wait(&s_full[b], (j >> 1) & 1);
             tc_fence_after();
-            tc_tmem_ld32_nowait(tm_s + b * 64 + lane_off, s0);
-            tc_tmem_ld32_nowait(tm_s + b * 64 + 32 + lane_off, s1);
-            tc_tmem_wait_ld();
+            tc_tmem_ld32(tm_s + b * 64 + lane_off, sv);
             tc_fence_before();
             tc_mbar_arrive(&s_empty[b]);
 
             float mx = -1e30f;
+            if (k0 >= lo_max && k0 + FA_BK - 1 <= hi_min) {             /* interior block (uniform over the CTA) */
 #pragma unroll
-            for (int c = 0; c < 32; c++) {
-                float a = __uint_as_float(s0[c]) * scale, bq = __uint_as_float(s1[c]) * scale;
-                a = (c >= c_lo && c <= c_hi) ? a : -1e30f;
-                bq = (c + 32 >= c_lo && c + 32 <= c_hi) ? bq : -1e30f;
-                s0[c] = __float_as_uint(a); s1[c] = __float_as_uint(bq);
-                mx = fmaxf(mx, fmaxf(a, bq));
+                for (int c = 0; c < 32; c++) {
+                    const float a = __uint_as_float(sv[c]) * scale;
+                    sv[c] = __float_as_uint(a);
+                    mx = fmaxf(mx, a);
+                }
+            } else {
+                const int c_lo = lo - k0 - hf * 32, c_hi = hi - k0 - hf * 32;
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    float a = __uint_as_float(sv[c]) * scale;
+                    a = (c >= c_lo && c <= c_hi) ? a : -1e30f;
+                    sv[c] = __float_as_uint(a);
+                    mx = fmaxf(mx, a);
+                }
             }
+            xch[(b * 2 + hf) * FA_BQ + r] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mx = fmaxf(mx, xch[(b * 2 + (hf ^ 1)) * FA_BQ + r]);
             const float mn = fmaxf(m, mx);
-            const float alpha = expf(m - mn);
+            const float alpha = fa_exp(m - mn);
             float rs = 0.f;
 #pragma unroll
             for (int c = 0; c < 32; c++) {
-                const float a = __uint_as_float(s0[c]), bq = __uint_as_float(s1[c]);
-                const float pa = a > -1e29f ? expf(a - mn) : 0.f;
-                const float pb = bq > -1e29f ? expf(bq - mn) : 0.f;
-                s0[c] = __float_as_uint(pa); s1[c] = __float_as_uint(pb);
-                rs += pa + pb;
+                const float a = __uint_as_float(sv[c]);
+                const float p = a > -1e29f ? fa_exp(a - mn) : 0.f;
+                sv[c] = __float_as_uint(p);
+                rs += p;
             }
             l = l * alpha + rs;
             m = mn;
@@ -248,19 +272,18 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             if (j >= 1) tc_mbar_wait(&o_full[b ^ 1], ((j - 1) >> 1) & 1);     /* (P V)(j-1) retired: P may be overwritten */
             /* P(j) -> three bf16 planes, rows of 128 B, 16-byte chunk c of row r at chunk (c ^ (r & 7)) (SWIZZLE_128B) */
 #pragma unroll
-            for (int cc = 0; cc < 8; cc++) {
+            for (int c4 = 0; c4 < 4; c4++) {
                 uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
                 for (int e2 = 0; e2 < 4; e2++) {
-                    const int c = cc * 8 + e2 * 2;
-                    const float x = __uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]);
-                    const float y = __uint_as_float(c + 1 < 32 ? s0[(c + 1) & 31] : s1[(c + 1) & 31]);
-                    uint32_t x0, x1, x2, y0, y1, y2;
-                    tc_split3(x, x0, x1, x2);
-                    tc_split3(y, y0, y1, y2);
-                    w0[e2] = x0 | (y0 << 16); w1[e2] = x1 | (y1 << 16); w2[e2] = x2 | (y2 << 16);
+                    float x = __uint_as_float(sv[c4 * 8 + e2 * 2]), y = __uint_as_float(sv[c4 * 8 + e2 * 2 + 1]);
+                    w0[e2] = tc_pack_bf16x2(x, y);
+                    x -= vb_bf16_lo(w0[e2]); y -= vb_bf16_hi(w0[e2]);   /* exact */
+                    w1[e2] = tc_pack_bf16x2(x, y);
+                    x -= vb_bf16_lo(w1[e2]); y -= vb_bf16_hi(w1[e2]);
+                    w2[e2] = tc_pack_bf16x2(x, y);
                 }
-                const uint32_t dst = prow + ((cc ^ sw) << 4);
+                const uint32_t dst = prow + (((hf * 4 + c4) ^ sw) << 4);
                 fa_sts128(dst, w0);
                 fa_sts128(dst + FA_QPLANE, w1);
                 fa_sts128(dst + 2 * FA_QPLANE, w2);
@@ -270,39 +293,55 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
 
             if (j >= 1) {                                               /* O = O * alpha(j-1) + (P V)(j-1) */
                 tc_fence_after();
-                tc_tmem_ld32_nowait(tm_o + (b ^ 1) * 64 + lane_off, s0);
-                tc_tmem_ld32_nowait(tm_o + (b ^ 1) * 64 + 32 + lane_off, s1);
-                tc_tmem_wait_ld();
+                tc_tmem_ld32(tm_o + (b ^ 1) * 64 + lane_off, sv);
                 tc_fence_before();
                 tc_mbar_arrive(&o_empty[b ^ 1]);
 #pragma unroll
-                for (int d = 0; d < 32; d++) {
-                    o[d] = fmaf(o[d], alpha_prev, __uint_as_float(s0[d]));
-                    o[d + 32] = fmaf(o[d + 32], alpha_prev, __uint_as_float(s1[d]));
-                }
+                for (int d = 0; d < 32; d++) o[d] = fmaf(o[d], alpha_prev, __uint_as_float(sv[d]));
             }
             alpha_prev = alpha;
         }
         if (nb > 0) {
             const int b = (nb - 1) & 1;
-            uint32_t s0[32], s1[32];
+            uint32_t sv[32];
             tc_mbar_wait(&o_full[b], ((nb - 1) >> 1) & 1);
             tc_fence_after();
-            tc_tmem_ld32_nowait(tm_o + b * 64 + lane_off, s0);
-            tc_tmem_ld32_nowait(tm_o + b * 64 + 32 + lane_off, s1);
-            tc_tmem_wait_ld();
+            tc_tmem_ld32(tm_o + b * 64 + lane_off, sv);
 #pragma unroll
-            for (int d = 0; d < 32; d++) {
-                o[d] = fmaf(o[d], alpha_prev, __uint_as_float(s0[d]));
-                o[d + 32] = fmaf(o[d + 32], alpha_prev, __uint_as_float(s1[d]));
-            }
+            for (int d = 0; d < 32; d++) o[d] = fmaf(o[d], alpha_prev, __uint_as_float(sv[d]));
         }
+        /* row sum = the two halves' partial sums (same running maximum in both) */
+        float *lx = reinterpret_cast<float *>(sm + FA_OFF_XCH) + 4 * FA_BQ;
+        lx[hf * FA_BQ + r] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l += lx[(hf ^ 1) * FA_BQ + r];
         if (q0 + r < seq_q) {
             const float inv = l > 0.f ? 1.0f / l : 0.f;
-            float *dst = out + (size_t)(q0 + r) * ldo + hoff;
+            if (oplanes) {
+                uint16_t *dst = oplanes + (size_t)(q0 + r) * cols + hoff + hf * 32;
+                const size_t plane = (size_t)seq_q * cols;
 #pragma unroll
-            for (int d = 0; d < FA_HD; d += 4)
-                *reinterpret_cast<float4 *>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+                for (int d = 0; d < 32; d += 8) {
+                    uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; e2++) {
+                        float x = o[d + 2 * e2] * inv, y = o[d + 2 * e2 + 1] * inv;
+                        w0[e2] = tc_pack_bf16x2(x, y);
+                        x -= vb_bf16_lo(w0[e2]); y -= vb_bf16_hi(w0[e2]);
+                        w1[e2] = tc_pack_bf16x2(x, y);
+                        x -= vb_bf16_lo(w1[e2]); y -= vb_bf16_hi(w1[e2]);
+                        w2[e2] = tc_pack_bf16x2(x, y);
+                    }
+                    *reinterpret_cast<uint4 *>(dst + d) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+                    *reinterpret_cast<uint4 *>(dst + d + plane) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                    *reinterpret_cast<uint4 *>(dst + d + 2 * plane) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+                }
+            } else {
+                float *dst = out + (size_t)(q0 + r) * ldo + hoff + hf * 32;
+#pragma unroll
+                for (int d = 0; d < 32; d += 4)
+                    *reinterpret_cast<float4 *>(dst + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+            }
         }
     }
     tc_fence_before();
@@ -325,17 +364,14 @@ int vb_attn_tc_usable(int seq_q, int seq_k, int n_heads, int n_kv_heads, int hea
            ((n_heads * head_dim) % 64) == 0;
 }
 
-void vb_attention_tc(VbEngine *e, float *out, int ldo, const float *Q, int ldq, const float *K, const float *V, int ldkv,
-                     int seq_q, int seq_k, int n_heads, float scale, int window, int q_offset) {
+/* V^T planes, tensor maps, launch.  qp: [3][seq_q][cols], kp: [3][seq_k][cols] complete. */
+static void attn_tc_launch(VbEngine *e, float *out, int ldo, const uint16_t *qp, const uint16_t *kp, const float *V, int ldkv,
+                           int seq_q, int seq_k, int n_heads, float scale, int window, int q_offset, uint16_t *oplanes) {
     static unsigned int attr_done = 0;                                  /* one bit per device */
     const unsigned int dev_bit = 1u << (e->device & 31);
     const int cols = n_heads * FA_HD;
     const int nk_pad = (seq_k + 63) & ~63;
-    uint16_t *qp = (uint16_t *)vb_ws(e, VB_WS_ATT_QP, (size_t)3 * seq_q * cols * 2 + 256);
-    uint16_t *kp = (uint16_t *)vb_ws(e, VB_WS_ATT_KP, (size_t)3 * seq_k * cols * 2 + 256);
     uint16_t *vt = (uint16_t *)vb_ws(e, VB_WS_ATT_VT, (size_t)3 * cols * nk_pad * 2 + 256);
-    vb_tc_split_planes(e, Q, ldq, seq_q, cols, 3, qp);
-    vb_tc_split_planes(e, K, ldkv, seq_k, cols, 3, kp);
     dim3 tg(nk_pad / 64, cols / 32);
     k_vt_planes<<<tg, 256, 0, e->stream>>>(V, ldkv, seq_k, cols, nk_pad, vt);
     VB_CUDA_OK(cudaGetLastError());
@@ -348,7 +384,40 @@ void vb_attention_tc(VbEngine *e, float *out, int ldo, const float *Q, int ldq, 
         attr_done |= dev_bit;
     }
     dim3 grid((seq_q + FA_BQ - 1) / FA_BQ, n_heads);
-    k_attn_tc<<<grid, FA_THREADS, FA_SMEM_BYTES, e->stream>>>(tmQ, tmK, tmV, out, ldo, seq_q, seq_k, cols, scale, window, q_offset);
+    k_attn_tc<<<grid, FA_THREADS, FA_SMEM_BYTES, e->stream>>>(tmQ, tmK, tmV, out, ldo, seq_q, seq_k, cols, scale, window, q_offset, oplanes);
     VB_CUDA_OK(cudaGetLastError());
-    vb_launch_count(e, 4);
+    vb_launch_count(e, 2);
+}
+
+/* the plane buffers of a call: the same sizes wherever they are requested, so a producer's rows survive until the consumer */
+uint16_t *vb_attn_tc_qplanes(VbEngine *e, int seq_q, int n_heads) {
+    return (uint16_t *)vb_ws(e, VB_WS_ATT_QP, (size_t)3 * seq_q * n_heads * FA_HD * 2 + 256);
+}
+uint16_t *vb_attn_tc_kplanes(VbEngine *e, int seq_k, int n_heads) {
+    return (uint16_t *)vb_ws(e, VB_WS_ATT_KP, (size_t)3 * seq_k * n_heads * FA_HD * 2 + 256);
+}
+
+void vb_attention_tc(VbEngine *e, float *out, int ldo, const float *Q, int ldq, const float *K, const float *V, int ldkv,
+                     int seq_q, int seq_k, int n_heads, float scale, int window, int q_offset, uint16_t *oplanes) {
+    const int cols = n_heads * FA_HD;
+    uint16_t *qp = vb_attn_tc_qplanes(e, seq_q, n_heads);
+    uint16_t *kp = vb_attn_tc_kplanes(e, seq_k, n_heads);
+    vb_tc_split_planes(e, Q, ldq, seq_q, cols, 3, qp);
+    vb_tc_split_planes(e, K, ldkv, seq_k, cols, 3, kp);
+    vb_launch_count(e, 2);
+    attn_tc_launch(e, out, ldo, qp, kp, V, ldkv, seq_q, seq_k, n_heads, scale, window, q_offset, oplanes);
+}
+
+/* Q planes and the K planes of the call's own rows [q_offset, seq_k) were written by the wq|wk|wv epilogue (vb_gemm_tc_qkv_rope);
+ * the rows before them (cache tail / halo of a sharded run, f32 in K) are split here. */
+void vb_attention_tc_pre(VbEngine *e, float *out, int ldo, const float *K, const float *V, int ldkv,
+                         int seq_q, int seq_k, int n_heads, float scale, int window, int q_offset, uint16_t *oplanes) {
+    const int cols = n_heads * FA_HD;
+    uint16_t *qp = vb_attn_tc_qplanes(e, seq_q, n_heads);
+    uint16_t *kp = vb_attn_tc_kplanes(e, seq_k, n_heads);
+    if (q_offset > 0) {
+        vb_tc_split_planes_strided(e, K, ldkv, q_offset, cols, 3, kp, (size_t)seq_k * cols);
+        vb_launch_count(e, 1);
+    }
+    attn_tc_launch(e, out, ldo, qp, kp, V, ldkv, seq_q, seq_k, n_heads, scale, window, q_offset, oplanes);
 }

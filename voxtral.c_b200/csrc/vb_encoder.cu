@@ -45,21 +45,51 @@ static void enc_alloc_tail(VbEngine *e) {
  *                SwiGLU -> w2(+bias)+res.  x: [M,1280] updated in place. */
 extern "C" void vb_enc_layer_qkv_dev(VbEngine *e, int l, const float *x, int M, int pos0, float *kb, float *vb, int row_off) {
     const VbEncLayerDev &w = e->enc[l];
-    float *xn  = vb_ws(e, 1, (size_t)M * ENC_DIM * 4);
     float *qkv = vb_ws(e, 2, (size_t)M * VB_ENC_QKV * 4);
-    vb_rmsnorm_rows(e, xn, x, w.attn_norm, nullptr, M, ENC_DIM, VOX_ENC_NORM_EPS);
-    vb_gemm_bf16w(e, xn, ENC_DIM, w.wqkv, w.bqkv, qkv, VB_ENC_QKV, M, VB_ENC_QKV, ENC_DIM, VB_EPI_STORE);
+    if (vb_gemm_tc_fused_ok(M)) {                                 /* long calls: RMSNorm writes the GEMM's bf16 planes directly */
+        uint16_t *xnp = (uint16_t *)vb_ws(e, VB_WS_ENC_XNP, (size_t)3 * M * ENC_DIM * 2 + 256);
+        vb_rmsnorm_rows_planes(e, xnp, x, w.attn_norm, M, ENC_DIM, VOX_ENC_NORM_EPS);
+        if (vb_gemm_tc_qkv_ok(M) && vb_attn_tc_enabled()) {
+            /* bias + RoPE + K/V append + the attention's Q/K planes as the GEMM's epilogue: no f32 qkv, no k_rope_split */
+            vb_gemm_tc_qkv_rope(e, xnp, w.wqkv, w.bqkv, M, ENC_DIM, e->d_enc_inv_freq, pos0,
+                                vb_attn_tc_qplanes(e, M, VOX_ENC_HEADS), vb_attn_tc_kplanes(e, row_off + M, VOX_ENC_HEADS),
+                                kb, vb, row_off, row_off + M);
+            return;
+        }
+        vb_gemm_tc_planes(e, xnp, w.wqkv, w.bqkv, qkv, VB_ENC_QKV, M, VB_ENC_QKV, ENC_DIM, VB_EPI_STORE, nullptr);
+    } else {
+        float *xn  = vb_ws(e, 1, (size_t)M * ENC_DIM * 4);
+        vb_rmsnorm_rows(e, xn, x, w.attn_norm, nullptr, M, ENC_DIM, VOX_ENC_NORM_EPS);
+        vb_gemm_bf16w(e, xn, ENC_DIM, w.wqkv, w.bqkv, qkv, VB_ENC_QKV, M, VB_ENC_QKV, ENC_DIM, VB_EPI_STORE);
+    }
     vb_rope_split(e, qkv, VB_ENC_QKV, M, VOX_ENC_HEADS, VOX_ENC_KV_HEADS, VOX_ENC_HEAD_DIM,
                   e->d_enc_inv_freq, pos0, kb, vb, row_off, -1);
 }
 
 extern "C" void vb_enc_layer_rest_dev(VbEngine *e, int l, float *x, int M, const float *kb, const float *vb, int q_off) {
     const VbEncLayerDev &w = e->enc[l];
-    float *xn  = vb_ws(e, 1, (size_t)M * ENC_DIM * 4);
     float *qkv = vb_ws(e, 2, (size_t)M * VB_ENC_QKV * 4);           /* q part written by the first half */
+    const float scale = 1.0f / sqrtf((float)VOX_ENC_HEAD_DIM);
+    if (vb_gemm_tc_fused_ok(M) && vb_attn_tc_enabled() &&
+        vb_attn_tc_usable(M, q_off + M, VOX_ENC_HEADS, VOX_ENC_KV_HEADS, VOX_ENC_HEAD_DIM, VB_ENC_QKV, VB_ENC_ATT, VB_ENC_ATT)) {
+        /* long calls: every producer writes the next GEMM's A operand as bf16 planes (no f32 round trip, no k_split_planes):
+         * attention -> wo, RMSNorm -> w1|w3, SiLU(g)*u -> w2.  Same values as the unfused path below, bit for bit. */
+        uint16_t *attp = (uint16_t *)vb_ws(e, VB_WS_ENC_ATTP, (size_t)3 * M * VB_ENC_ATT * 2 + 256);
+        uint16_t *xnp  = (uint16_t *)vb_ws(e, VB_WS_ENC_XNP, (size_t)3 * M * ENC_DIM * 2 + 256);
+        uint16_t *gp   = (uint16_t *)vb_ws(e, VB_WS_ENC_GP, (size_t)3 * M * ENC_HID * 2 + 256);
+        if (vb_gemm_tc_qkv_ok(M))                                /* Q planes and the new rows' K planes are already there */
+            vb_attention_tc_pre(e, nullptr, 0, kb, vb, VB_ENC_ATT, M, q_off + M, VOX_ENC_HEADS, scale, ENC_WIN, q_off, attp);
+        else
+            vb_attention_tc(e, nullptr, 0, qkv, VB_ENC_QKV, kb, vb, VB_ENC_ATT, M, q_off + M, VOX_ENC_HEADS, scale, ENC_WIN, q_off, attp);
+        vb_gemm_tc_planes(e, attp, w.wo, w.bo, x, ENC_DIM, M, ENC_DIM, VB_ENC_ATT, VB_EPI_RESIDUAL, nullptr);
+        vb_rmsnorm_rows_planes(e, xnp, x, w.ffn_norm, M, ENC_DIM, VOX_ENC_NORM_EPS);
+        vb_gemm_tc_planes(e, xnp, w.w13, nullptr, nullptr, 0, M, 2 * ENC_HID, ENC_DIM, VB_EPI_SWIGLU, gp);
+        vb_gemm_tc_planes(e, gp, w.w2, w.b2, x, ENC_DIM, M, ENC_DIM, ENC_HID, VB_EPI_RESIDUAL, nullptr);
+        return;
+    }
+    float *xn  = vb_ws(e, 1, (size_t)M * ENC_DIM * 4);
     float *att = vb_ws(e, 3, (size_t)M * VB_ENC_ATT * 4);
     float *g   = vb_ws(e, 4, (size_t)M * ENC_HID * 4);
-    const float scale = 1.0f / sqrtf((float)VOX_ENC_HEAD_DIM);
     vb_attention_rows(e, att, VB_ENC_ATT, qkv, VB_ENC_QKV, kb, vb, VB_ENC_ATT, M, q_off + M,
                       VOX_ENC_HEADS, VOX_ENC_KV_HEADS, VOX_ENC_HEAD_DIM, scale, ENC_WIN, q_off);
     vb_gemm_bf16w(e, att, VB_ENC_ATT, w.wo, w.bo, x, ENC_DIM, M, ENC_DIM, VB_ENC_ATT, VB_EPI_RESIDUAL);

@@ -40,6 +40,10 @@
 #define VB_WS_ATT_QP 25      /* 25-27: bf16 planes of Q, K and V^T for the tcgen05 attention (vb_attn_tc.cu) */
 #define VB_WS_ATT_KP 26
 #define VB_WS_ATT_VT 27
+#define VB_WS_ENC_XNP 28     /* 28-30: bf16 planes written by the fused encoder producers (RMSNorm, attention, SwiGLU) */
+#define VB_WS_ENC_ATTP 29
+#define VB_WS_ENC_GP 30
+#define VB_WS_ENC_ROPE 31    /* [M][32] (cos, sin) table of the fused wq|wk|wv epilogue (vb_gemm_tc.cu) */
 
 /* Error boundary.  Inside the library a failed CUDA call (cudaMalloc out of memory, a launch error...) reports through
  * vb_cuda_fail().  Public entry points that have an error return in the reference -- vox_load -> NULL (voxtral.c:132-158),

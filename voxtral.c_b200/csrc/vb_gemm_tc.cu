@@ -33,13 +33,12 @@
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 
 /* ------------------------------------------------------------------ activation split: f32 [M,lda] -> bf16 planes [nsplit][M][K] */
-__global__ void k_split_planes(const float *__restrict__ A, int lda, int M, int K, int nsplit, uint16_t *__restrict__ planes) {
+__global__ void k_split_planes(const float *__restrict__ A, int lda, int M, int K, int nsplit, uint16_t *__restrict__ planes, size_t plane) {
     long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (idx >= (long long)M * K) return;
     int m = (int)(idx / K), k = (int)(idx % K);                       /* K % 4 == 0 */
     const float4 v = *reinterpret_cast<const float4 *>(A + (size_t)m * lda + k);
     float x[4] = { v.x, v.y, v.z, v.w };
-    const size_t plane = (size_t)M * K;
     uint16_t out[3][4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -59,10 +58,14 @@ __global__ void k_split_planes(const float *__restrict__ A, int lda, int M, int 
     }
 }
 
-void vb_tc_split_planes(VbEngine *e, const float *A, int lda, int M, int K, int nsplit, uint16_t *planes) {
+void vb_tc_split_planes_strided(VbEngine *e, const float *A, int lda, int M, int K, int nsplit, uint16_t *planes, size_t plane_elems) {
+    if (M <= 0) return;
     long long quads = ((long long)M * K + 3) / 4;
-    k_split_planes<<<(int)((quads + 255) / 256), 256, 0, e->stream>>>(A, lda, M, K, nsplit, planes);
+    k_split_planes<<<(int)((quads + 255) / 256), 256, 0, e->stream>>>(A, lda, M, K, nsplit, planes, plane_elems);
     VB_CUDA_OK(cudaGetLastError());
+}
+void vb_tc_split_planes(VbEngine *e, const float *A, int lda, int M, int K, int nsplit, uint16_t *planes) {
+    vb_tc_split_planes_strided(e, A, lda, M, K, nsplit, planes, (size_t)M * K);
 }
 
 /* ------------------------------------------------------------------ the GEMM */
@@ -187,15 +190,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
  *     is already accumulating tile i+1.
  */
 #define T2_BN 256
+/* Calls with fewer rows stay on k_gemm_tc: with <= 4 row tiles there is nothing to pipeline across.  The two kernels add the
+ * plane products in a different order (here k-block-major, there plane-major), so their results differ at the level of the
+ * tensor core's f32 accumulation (~1e-5 of the row scale) -- both inside the stated tolerance, but not bit-identical.  Measured
+ * consequence (gpurun_out/r02c_stream_*.log): with the persistent kernel on the 1-s feeds of the 172-s continuous fixture, the
+ * near-tie at step 1864 (reference top-2 margin 2.7e-5) decodes to the other id; with the plane-major order all 2154 ids match.
+ * The persistent kernel therefore takes the long one-shot / sharded calls, where its throughput matters. */
+#define T2_MIN_M 512
 #define T2_STAGES 2
 #define T2_W_BYTES (T2_BN * TC_BK * 2)                      /* 32 KB */
 #define T2_STAGE_BYTES (T2_W_BYTES + 3 * TC_A_BYTES)        /* 80 KB */
 #define T2_SMEM_BYTES (T2_STAGES * T2_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 
+/* What an epilogue of the persistent kernel writes besides / instead of C (fused producers of the long encoder calls). */
+struct VbTcSink {
+    uint16_t *oplanes;              /* SWIGLU: SiLU(g)*u as [3][M][N/2] bf16 planes (the A operand of w2) instead of C */
+    /* QKV_ROPE (encoder wq|wk|wv, head_dim 64, 2048 columns per block): bias, RoPE, then
+     *   q -> qplanes [3][M][2048];  k -> kdst f32 rows (dst_row0 + m) AND kplanes [3][seq_k][2048] rows (dst_row0 + m);  v -> vdst f32 */
+    const float2 *rope;             /* [M][32] (cos, sin) of angle (float)(pos0 + m) * inv_freq[d] */
+    uint16_t *qplanes, *kplanes;
+    float *kdst, *vdst;
+    int dst_row0, seq_k;
+};
+#define VB_EPI_QKV_ROPE 4
+
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-           const float *__restrict__ bias, float *__restrict__ C, int ldc, int M, int N, int K, int nsplit) {
+           const float *__restrict__ bias, float *__restrict__ C, int ldc, int M, int N, int K, int nsplit,
+           const VbTcSink sink) {
+    uint16_t *__restrict__ oplanes = sink.oplanes;
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(tiles + T2_STAGES * T2_STAGE_BYTES);
@@ -280,7 +304,79 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 uint32_t r[32];
                 tc_tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * T2_BN + c0), r);
                 if (row < M) {
-                    if (EPI == VB_EPI_SWIGLU) {
+                    if (EPI == VB_EPI_QKV_ROPE) {
+                        /* voxtral_encoder.c:533-553: q/k/v = x W^T + b, RoPE on q and k, k and v appended to the cache.  32 columns =
+                         * half a head = 16 (even, odd) pairs; arithmetic as k_rope_split: y0 = fma(x0, c, -(x1 s)), y1 = fma(x0, s, x1 c) */
+                        const int n = n0 + c0, region = n >> 11, c = n & 2047;
+                        float x[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bv = *reinterpret_cast<const float4 *>(bias + n + j);
+                            x[j] = __uint_as_float(r[j]) + bv.x; x[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+                            x[j + 2] = __uint_as_float(r[j + 2]) + bv.z; x[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+                        }
+                        if (region == 2) {
+                            float *dst = sink.vdst + (size_t)(sink.dst_row0 + row) * 2048 + c;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                        } else {
+                            const float2 *t = sink.rope + (size_t)row * 32 + ((c & 63) >> 1);
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                const float2 cs = t[j];
+                                const float x0 = x[2 * j], x1 = x[2 * j + 1];
+                                x[2 * j]     = __fmaf_rn(x0, cs.x, -__fmul_rn(x1, cs.y));
+                                x[2 * j + 1] = __fmaf_rn(x0, cs.y, __fmul_rn(x1, cs.x));
+                            }
+                            uint16_t *pd; size_t plane;
+                            if (region == 1) {
+                                float *dst = sink.kdst + (size_t)(sink.dst_row0 + row) * 2048 + c;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+                                pd = sink.kplanes + (size_t)(sink.dst_row0 + row) * 2048 + c; plane = (size_t)sink.seq_k * 2048;
+                            } else {
+                                pd = sink.qplanes + (size_t)row * 2048 + c; plane = (size_t)M * 2048;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+                                for (int e2 = 0; e2 < 4; e2++) {
+                                    float a = x[j + 2 * e2], b2 = x[j + 2 * e2 + 1];
+                                    w0[e2] = tc_pack_bf16x2(a, b2);
+                                    a -= vb_bf16_lo(w0[e2]); b2 -= vb_bf16_hi(w0[e2]);
+                                    w1[e2] = tc_pack_bf16x2(a, b2);
+                                    a -= vb_bf16_lo(w1[e2]); b2 -= vb_bf16_hi(w1[e2]);
+                                    w2[e2] = tc_pack_bf16x2(a, b2);
+                                }
+                                *reinterpret_cast<uint4 *>(pd + j) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+                                *reinterpret_cast<uint4 *>(pd + j + plane) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                                *reinterpret_cast<uint4 *>(pd + j + 2 * plane) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+                            }
+                        }
+                    } else if (EPI == VB_EPI_SWIGLU && oplanes != nullptr) {
+                        /* 16 outputs of this row -> three bf16 planes, 32 B each */
+                        const size_t nh = (size_t)(N >> 1);
+                        uint16_t *dst = oplanes + (size_t)row * nh + ((n0 + c0) >> 1);
+                        uint32_t w0[8], w1[8], w2[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float x = vb_silu(__uint_as_float(r[4 * j + 0])) * __uint_as_float(r[4 * j + 1]);
+                            float y = vb_silu(__uint_as_float(r[4 * j + 2])) * __uint_as_float(r[4 * j + 3]);
+                            w0[j] = tc_pack_bf16x2(x, y);
+                            x -= vb_bf16_lo(w0[j]); y -= vb_bf16_hi(w0[j]);
+                            w1[j] = tc_pack_bf16x2(x, y);
+                            x -= vb_bf16_lo(w1[j]); y -= vb_bf16_hi(w1[j]);
+                            w2[j] = tc_pack_bf16x2(x, y);
+                        }
+                        const size_t plane = (size_t)M * nh;
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+                        *reinterpret_cast<uint4 *>(dst + 8) = make_uint4(w0[4], w0[5], w0[6], w0[7]);
+                        *reinterpret_cast<uint4 *>(dst + plane) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+                        *reinterpret_cast<uint4 *>(dst + plane + 8) = make_uint4(w1[4], w1[5], w1[6], w1[7]);
+                        *reinterpret_cast<uint4 *>(dst + 2 * plane) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+                        *reinterpret_cast<uint4 *>(dst + 2 * plane + 8) = make_uint4(w2[4], w2[5], w2[6], w2[7]);
+                    } else if (EPI == VB_EPI_SWIGLU) {
                         float *dst = C + (size_t)row * ldc + ((n0 + c0) >> 1);
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -362,13 +458,21 @@ static int gemm_variant(void) {
     return v;
 }
 
-void vb_gemm_tc(VbEngine *e, const float *A, int lda, const uint16_t *W, const float *bias, float *C, int ldc,
-                int M, int N, int K, int epi) {
+/* Fused producers (RMSNorm, attention and SwiGLU epilogues writing bf16 planes directly) are used for the calls that take
+ * the persistent kernel; VOX_CUDA_FUSE=0 keeps the separate k_split_planes passes (A/B, validation). */
+int vb_gemm_tc_fused_ok(int M) {
+    const char *s = getenv("VOX_CUDA_FUSE");                          /* read per call: a test flips it between two passes */
+    const char *g = getenv("VOX_CUDA_GEMM");
+    return !(s && s[0] == '0') && gemm_variant() == 2 && !(g && !strcmp(g, "simt")) && M >= T2_MIN_M;
+}
+
+/* The GEMM on activations that are already split: planes [3][M][K] bf16 (plane p, row m at (p*M + m)*K).
+ * oplanes (SWIGLU, persistent kernel only): the result is written as [3][M][N/2] bf16 planes instead of C. */
+void vb_gemm_tc_planes(VbEngine *e, const uint16_t *planes, const uint16_t *W, const float *bias, float *C, int ldc,
+                       int M, int N, int K, int epi, uint16_t *oplanes) {
     static unsigned int attr_done = 0;                              /* one bit per device: function attributes are per device */
     const unsigned int dev_bit = 1u << (e->device & 31);
     const int nsplit = vb_gemm_nsplit();
-    uint16_t *planes = (uint16_t *)vb_ws(e, VB_WS_GEMM_PLANES, (size_t)nsplit * M * K * 2 + 256);
-    vb_tc_split_planes(e, A, lda, M, K, nsplit, planes);
     if (!(attr_done & dev_bit)) {
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<VB_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<VB_EPI_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -378,22 +482,27 @@ void vb_gemm_tc(VbEngine *e, const float *A, int lda, const uint16_t *W, const f
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc2<VB_EPI_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc2<VB_EPI_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
         VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc2<VB_EPI_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+        VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc2<VB_EPI_QKV_ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
         attr_done |= dev_bit;
     }
     CUtensorMap tmA, tmW;
     vb_tc_make_map(&tmA, planes, (uint64_t)K, (uint64_t)nsplit * M, (uint64_t)K * 2, TC_BM);
     dim3 block(TC_THREADS);
-    if (gemm_variant() == 2 && (N % T2_BN) == 0) {
+    VbTcSink sink;
+    memset(&sink, 0, sizeof sink);
+    sink.oplanes = oplanes;
+    if (gemm_variant() == 2 && (N % T2_BN) == 0 && M >= T2_MIN_M) {
         vb_tc_make_map(&tmW, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, T2_BN);
         const int total = (N / T2_BN) * ((M + TC_BM - 1) / TC_BM);
         dim3 grid(total < e->sm_count ? total : e->sm_count);
         switch (epi) {
-        case VB_EPI_STORE:    k_gemm_tc2<VB_EPI_STORE><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit); break;
-        case VB_EPI_GELU:     k_gemm_tc2<VB_EPI_GELU><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit); break;
-        case VB_EPI_RESIDUAL: k_gemm_tc2<VB_EPI_RESIDUAL><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit); break;
-        case VB_EPI_SWIGLU:   k_gemm_tc2<VB_EPI_SWIGLU><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit); break;
+        case VB_EPI_STORE:    k_gemm_tc2<VB_EPI_STORE><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit, sink); break;
+        case VB_EPI_GELU:     k_gemm_tc2<VB_EPI_GELU><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit, sink); break;
+        case VB_EPI_RESIDUAL: k_gemm_tc2<VB_EPI_RESIDUAL><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit, sink); break;
+        case VB_EPI_SWIGLU:   k_gemm_tc2<VB_EPI_SWIGLU><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit, sink); break;
         }
     } else {
+        if (oplanes) VB_FAIL("vb_gemm_tc_planes: plane output needs the persistent kernel");
         vb_tc_make_map(&tmW, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, TC_BN);
         dim3 grid(N / TC_BN, (M + TC_BM - 1) / TC_BM);
         switch (epi) {
@@ -403,6 +512,60 @@ void vb_gemm_tc(VbEngine *e, const float *A, int lda, const uint16_t *W, const f
         case VB_EPI_SWIGLU:   k_gemm_tc<VB_EPI_SWIGLU><<<grid, block, TC_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, C, ldc, M, N, K, nsplit); break;
         }
     }
+    VB_CUDA_OK(cudaGetLastError());
+    vb_launch_count(e, 1);
+}
+
+void vb_gemm_tc(VbEngine *e, const float *A, int lda, const uint16_t *W, const float *bias, float *C, int ldc,
+                int M, int N, int K, int epi) {
+    const int nsplit = vb_gemm_nsplit();
+    uint16_t *planes = (uint16_t *)vb_ws(e, VB_WS_GEMM_PLANES, (size_t)nsplit * M * K * 2 + 256);
+    vb_tc_split_planes(e, A, lda, M, K, nsplit, planes);
+    vb_launch_count(e, 1);
+    vb_gemm_tc_planes(e, planes, W, bias, C, ldc, M, N, K, epi, nullptr);
+}
+
+/* ------------------------------------------------------------------ encoder wq|wk|wv with RoPE + K/V append + Q/K planes as the epilogue */
+__global__ void k_rope_table(float2 *__restrict__ t, const float *__restrict__ inv_freq, int M, int half, int pos0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * half) return;
+    const int m = i / half, d = i % half;
+    float sn, cs;
+    sincosf((float)(pos0 + m) * inv_freq[d], &sn, &cs);                /* the angle and the call of k_rope_split (vb_ops.cu) */
+    t[i] = make_float2(cs, sn);
+}
+
+int vb_gemm_tc_qkv_ok(int M) {
+    const char *s = getenv("VOX_CUDA_FUSE_QKV");
+    return vb_gemm_tc_fused_ok(M) && !(s && s[0] == '0');
+}
+
+/* planes: RMSNorm output as [3][M][1280] planes.  q planes -> qplanes [3][M][2048]; rotated k -> kdst rows dst_row0.. (f32) and
+ * kplanes [3][seq_k][2048] rows dst_row0..; v -> vdst rows dst_row0.. (f32).  Encoder geometry only (32 heads x 64). */
+void vb_gemm_tc_qkv_rope(VbEngine *e, const uint16_t *planes, const uint16_t *W, const float *bias, int M, int K,
+                         const float *inv_freq, int pos0, uint16_t *qplanes, uint16_t *kplanes, float *kdst, float *vdst,
+                         int dst_row0, int seq_k) {
+    const int N = 3 * 2048, nsplit = vb_gemm_nsplit();
+    if (!bias || M < T2_MIN_M) VB_FAIL("vb_gemm_tc_qkv_rope: needs a bias and a long call");
+    float2 *table = (float2 *)vb_ws(e, VB_WS_ENC_ROPE, (size_t)M * 32 * sizeof(float2) + 256);
+    k_rope_table<<<(M * 32 + 255) / 256, 256, 0, e->stream>>>(table, inv_freq, M, 32, pos0);
+    VB_CUDA_OK(cudaGetLastError());
+    static unsigned int attr_done = 0;
+    const unsigned int dev_bit = 1u << (e->device & 31);
+    if (!(attr_done & dev_bit)) {
+        VB_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc2<VB_EPI_QKV_ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+        attr_done |= dev_bit;
+    }
+    CUtensorMap tmA, tmW;
+    vb_tc_make_map(&tmA, planes, (uint64_t)K, (uint64_t)nsplit * M, (uint64_t)K * 2, TC_BM);
+    vb_tc_make_map(&tmW, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, T2_BN);
+    VbTcSink sink;
+    memset(&sink, 0, sizeof sink);
+    sink.rope = table; sink.qplanes = qplanes; sink.kplanes = kplanes; sink.kdst = kdst; sink.vdst = vdst;
+    sink.dst_row0 = dst_row0; sink.seq_k = seq_k;
+    const int total = (N / T2_BN) * ((M + TC_BM - 1) / TC_BM);
+    dim3 grid(total < e->sm_count ? total : e->sm_count), block(TC_THREADS);
+    k_gemm_tc2<VB_EPI_QKV_ROPE><<<grid, block, T2_SMEM_BYTES, e->stream>>>(tmA, tmW, bias, nullptr, 0, M, N, K, nsplit, sink);
     VB_CUDA_OK(cudaGetLastError());
     vb_launch_count(e, 2);
 }

@@ -191,6 +191,45 @@ void vb_rmsnorm_rows(VbEngine *e, float *out, const float *x, const float *w, co
     vb_launch_count(e, 1);
 }
 
+/* The same normalisation written as three bf16 planes [3][rows][hidden] (x = p0 + p1 + p2, vb_tc.cuh): the A operand of the
+ * tcgen05 GEMM that follows, without the f32 round trip through HBM.  First loop identical to k_rmsnorm_rows (same partial
+ * sums, same rinv), so plane p0+p1+p2 of an element is exactly the f32 value k_rmsnorm_rows would have stored. */
+__global__ void __launch_bounds__(256)
+k_rmsnorm_rows_planes(uint16_t *__restrict__ planes, const float *__restrict__ x, const float *__restrict__ w, int rows, int hidden, float eps) {
+    __shared__ float red[8];
+    const float *xr = x + (size_t)blockIdx.x * hidden;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < hidden; i += 256) { float v = xr[i]; ss = fmaf(v, v, ss); }
+    ss = vb_warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tot += red[i];
+    float rinv = 1.0f / sqrtf(tot / (float)hidden + eps);
+    const size_t plane = (size_t)rows * hidden;
+    uint16_t *orow = planes + (size_t)blockIdx.x * hidden;
+    for (int i = 2 * threadIdx.x; i < hidden; i += 512) {               /* hidden is even */
+        float a = xr[i] * rinv * w[i], b = xr[i + 1] * rinv * w[i + 1];
+        uint32_t p0 = vb_pack_bf16x2(a, b);
+        a -= vb_bf16_lo(p0); b -= vb_bf16_hi(p0);
+        uint32_t p1 = vb_pack_bf16x2(a, b);
+        a -= vb_bf16_lo(p1); b -= vb_bf16_hi(p1);
+        uint32_t p2 = vb_pack_bf16x2(a, b);
+        *reinterpret_cast<uint32_t *>(orow + i) = p0;
+        *reinterpret_cast<uint32_t *>(orow + plane + i) = p1;
+        *reinterpret_cast<uint32_t *>(orow + 2 * plane + i) = p2;
+    }
+}
+
+void vb_rmsnorm_rows_planes(VbEngine *e, uint16_t *planes, const float *x, const float *w, int rows, int hidden, float eps) {
+    if (rows <= 0) return;
+    if (hidden & 1) VB_FAIL("vb_rmsnorm_rows_planes: odd hidden size");
+    k_rmsnorm_rows_planes<<<rows, 256, 0, e->stream>>>(planes, x, w, rows, hidden, eps);
+    VB_CUDA_OK(cudaGetLastError());
+    vb_launch_count(e, 1);
+}
+
 /* ======================================================================
  * RoPE + K/V scatter   (voxtral_kernels.c:488-526; cache writes voxtral_decoder.c:482-488,
  * voxtral_encoder.c:547-553).  angle = (float)pos * inv_freq[d] in f32, as :494-497.
@@ -502,7 +541,7 @@ void vb_attention_rows(VbEngine *e, float *out, int ldo, const float *Q, int ldq
                        int head_dim, float scale, int window, int q_offset) {
     if (seq_q <= 0) return;
     if (vb_attn_tc_enabled() && vb_attn_tc_usable(seq_q, seq_k, n_heads, n_kv_heads, head_dim, ldq, ldkv, ldo)) {
-        vb_attention_tc(e, out, ldo, Q, ldq, K, V, ldkv, seq_q, seq_k, n_heads, scale, window, q_offset);
+        vb_attention_tc(e, out, ldo, Q, ldq, K, V, ldkv, seq_q, seq_k, n_heads, scale, window, q_offset, nullptr);
         return;
     }
     if (head_dim == AT_HD && n_heads == n_kv_heads && seq_q >= 16 && (ldq % 4) == 0 && (ldkv % 4) == 0 && (ldo % 4) == 0) {

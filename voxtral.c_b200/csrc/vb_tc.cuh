@@ -83,6 +83,12 @@ __device__ __forceinline__ uint32_t f2bf_rne(float f) {
     uint32_t u = __float_as_uint(f);
     return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
 }
+/* two f32 -> one word of two bf16 (RNE, one F2FP): x in the low half, y in the high half */
+__device__ __forceinline__ uint32_t tc_pack_bf16x2(float x, float y) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
+    return d;
+}
 __device__ __forceinline__ void tc_split3(float x, uint32_t &p0, uint32_t &p1, uint32_t &p2) {
     p0 = f2bf_rne(x);
     float r = x - __uint_as_float(p0 << 16);                          /* exact: r and p0 share the leading bits */
@@ -93,6 +99,8 @@ __device__ __forceinline__ void tc_split3(float x, uint32_t &p0, uint32_t &p1, u
 
 /* f32 [M, lda] (K columns used, K % 4 == 0) -> bf16 planes [nsplit][M][K] on the engine's stream (vb_gemm_tc.cu) */
 void vb_tc_split_planes(VbEngine *e, const float *A, int lda, int M, int K, int nsplit, uint16_t *planes);
+/* the same with the planes plane_elems apart (rows of a larger [nsplit][rows][K] buffer) */
+void vb_tc_split_planes_strided(VbEngine *e, const float *A, int lda, int M, int K, int nsplit, uint16_t *planes, size_t plane_elems);
 
 /* host: 2-D bf16 tensor map with SWIZZLE_128B boxes of 64 columns x box_rows rows (vb_gemm_tc.cu) */
 void vb_tc_make_map(CUtensorMap *map, const void *base, uint64_t inner_elems, uint64_t rows, uint64_t row_pitch_bytes, uint32_t box_rows);
