@@ -78,6 +78,16 @@ def test_chunked_1s_tokens_match_reference(engine):
     check_against(g, ids, text)
 
 
+def test_two_long_feeds_match_oneshot_reference(engine):
+    """60 s fed as two 30-s halves: both encoder calls are long (persistent GEMM, tcgen05 attention, fused epilogues) and the
+    second one attends over the 750-row K/V tail of the first -- the cached rows go through the tail split of the K planes
+    (vb_attention_tc_pre), the path a sharded run's halo rows take.  Ids against the reference's one-shot trace of the clip."""
+    g = golden("synth_s60_oneshot")
+    pcm = read_wav_f32(synth_wav(60))
+    ids, text, _ = run_stream(engine, pcm, chunk=pcm.size // 2)
+    check_against(g, ids, text)
+
+
 def test_chunking_invariance(engine):
     """The incremental path must not depend on how the caller slices the audio (same mel frames, same
     conv/encoder rows up to f32 reordering) -- the tiny-interval run exercises the conv tails, the odd
