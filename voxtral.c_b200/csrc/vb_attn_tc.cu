@@ -162,9 +162,12 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && nb > 0) {
+        if (nb > 0) {                                                   /* whole warp converged; one elected lane issues */
             const uint32_t idesc = tc_idesc(FA_BQ, FA_BK);              /* M128 N64 for both products */
-            const uint32_t q_addr = s32(sm + FA_OFF_Q), p_addr = s32(sm + FA_OFF_P);
+            /* descriptors differ only in the start-address field (bits [0,14) = address >> 4): one base per operand tile,
+             * + 2 per k step of 16 elements (32 B), + the tile pitch >> 4 per plane */
+            const uint64_t dq = tc_smem_desc(s32(sm + FA_OFF_Q)), dp = tc_smem_desc(s32(sm + FA_OFF_P));
+            const uint64_t dk0 = tc_smem_desc(s32(sm + FA_OFF_K)), dv0 = tc_smem_desc(s32(sm + FA_OFF_V));
             tc_mbar_wait(q_full, 0);
             for (int j = -1; j < nb; j++) {
                 if (j + 1 < nb) {                                       /* S(j+1) = Q K(j+1)^T */
@@ -172,16 +175,19 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                     tc_mbar_wait(&k_full[s], (jj / FA_K_SLOTS) & 1);
                     tc_mbar_wait(&s_empty[b], ((jj >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t k_addr = s32(sm + FA_OFF_K + s * 3 * FA_KTILE);
+                    if (tc_elect_one()) {
+                        const uint64_t dk = dk0 + (uint64_t)(s * ((3 * FA_KTILE) >> 4));
 #pragma unroll
-                    for (int pr = 0; pr < 6; pr++) {
-                        const uint32_t a = q_addr + FA_PA(pr) * FA_QPLANE, bb = k_addr + FA_PB(pr) * FA_KTILE;
+                        for (int pr = 0; pr < 6; pr++) {
 #pragma unroll
-                        for (int k = 0; k < FA_HD / 16; k++)
-                            tc_umma_bf16(tm_s + b * 64, tc_smem_desc(a + k * 32), tc_smem_desc(bb + k * 32), idesc, (pr | k) ? 1u : 0u);
+                            for (int k = 0; k < FA_HD / 16; k++)
+                                tc_umma_bf16(tm_s + b * 64, dq + (uint64_t)(FA_PA(pr) * (FA_QPLANE >> 4) + 2 * k),
+                                             dk + (uint64_t)(FA_PB(pr) * (FA_KTILE >> 4) + 2 * k), idesc, (pr | k) ? 1u : 0u);
+                        }
+                        tc_umma_commit(&k_empty[s]);
+                        tc_umma_commit(&s_full[b]);
                     }
-                    tc_umma_commit(&k_empty[s]);
-                    tc_umma_commit(&s_full[b]);
+                    __syncwarp();
                 }
                 if (j >= 0) {                                           /* (P V)(j) */
                     const int s = j & 1, u = j >> 1;
@@ -189,16 +195,19 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                     tc_mbar_wait(p_full, j & 1);
                     tc_mbar_wait(&o_empty[s], (u & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t v_addr = s32(sm + FA_OFF_V + s * 3 * FA_VTILE);
+                    if (tc_elect_one()) {
+                        const uint64_t dv = dv0 + (uint64_t)(s * ((3 * FA_VTILE) >> 4));
 #pragma unroll
-                    for (int pr = 0; pr < 6; pr++) {
-                        const uint32_t a = p_addr + FA_PA(pr) * FA_QPLANE, bb = v_addr + FA_PB(pr) * FA_VTILE;
+                        for (int pr = 0; pr < 6; pr++) {
 #pragma unroll
-                        for (int k = 0; k < FA_BK / 16; k++)
-                            tc_umma_bf16(tm_o + s * 64, tc_smem_desc(a + k * 32), tc_smem_desc(bb + k * 32), idesc, (pr | k) ? 1u : 0u);
+                            for (int k = 0; k < FA_BK / 16; k++)
+                                tc_umma_bf16(tm_o + s * 64, dp + (uint64_t)(FA_PA(pr) * (FA_QPLANE >> 4) + 2 * k),
+                                             dv + (uint64_t)(FA_PB(pr) * (FA_VTILE >> 4) + 2 * k), idesc, (pr | k) ? 1u : 0u);
+                        }
+                        tc_umma_commit(&v_empty[s]);
+                        tc_umma_commit(&o_full[s]);
                     }
-                    tc_umma_commit(&v_empty[s]);
-                    tc_umma_commit(&o_full[s]);
+                    __syncwarp();
                 }
             }
         }

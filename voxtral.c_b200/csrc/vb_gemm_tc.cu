@@ -265,28 +265,31 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = tc_idesc(TC_BM, T2_BN);
-            int it = 0, tl = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x, tl++) {
-                const int ab = tl & 1;
-                tc_mbar_wait(&acc_empty[ab], ((tl >> 1) & 1) ^ 1);
+        /* the whole warp walks the schedule converged; one elected lane issues (vb_tc.cuh: tc_elect_one) */
+        const uint32_t idesc = tc_idesc(TC_BM, T2_BN);
+        const uint64_t d0 = tc_smem_desc(s32(tiles));                   /* + (byte offset >> 4) in the start-address field */
+        int it = 0, tl = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, tl++) {
+            const int ab = tl & 1;
+            tc_mbar_wait(&acc_empty[ab], ((tl >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)ab * T2_BN;
+            for (int kb = 0; kb < kblocks; kb++, it++) {
+                const int s = it % T2_STAGES;
+                tc_mbar_wait(&full[s], (it / T2_STAGES) & 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)ab * T2_BN;
-                for (int kb = 0; kb < kblocks; kb++, it++) {
-                    const int s = it % T2_STAGES;
-                    tc_mbar_wait(&full[s], (it / T2_STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t w_addr = s32(tiles + s * T2_STAGE_BYTES), a_addr = w_addr + T2_W_BYTES;
+                if (tc_elect_one()) {
+                    const uint64_t dw = d0 + (uint64_t)(s * (T2_STAGE_BYTES >> 4)), da = dw + (uint64_t)(T2_W_BYTES >> 4);
                     for (int p = 0; p < nsplit; p++) {
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; k++)
-                            tc_umma_bf16(d, tc_smem_desc(a_addr + p * TC_A_BYTES + k * 32), tc_smem_desc(w_addr + k * 32), idesc,
+                            tc_umma_bf16(d, da + (uint64_t)(p * (TC_A_BYTES >> 4) + 2 * k), dw + (uint64_t)(2 * k), idesc,
                                          (kb > 0 || p > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_umma_commit(&empty[s]);                          /* frees the stage when these MMAs retire */
+                    if (kb == kblocks - 1) tc_umma_commit(&acc_full[ab]);   /* accumulator complete */
                 }
-                tc_umma_commit(&acc_full[ab]);                          /* accumulator complete */
+                __syncwarp();
             }
         }
     } else {

@@ -38,6 +38,17 @@ __device__ __forceinline__ void tc_umma_bf16(uint32_t tmem_d, uint64_t adesc, ui
 __device__ __forceinline__ void tc_umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s32(bar)) : "memory");
 }
+/* One lane of a converged warp (cute::elect_one_sync).  The MMA / TMA issue loops run with the whole warp converged and only the
+ * issuing instructions under this predicate: descriptors and loop state then live in uniform registers.  With the loop inside an
+ * `if (lane == 0)` the compiler has to move every descriptor into uniform registers through an elect/broadcast sequence
+ * (9-14 instructions per tcgen05.mma): harmless at 12 MMAs per 1536 cycles (GEMM), the bottleneck at 48 short MMAs per key block
+ * (attention, profiles/r02_encoder.md). */
+__device__ __forceinline__ uint32_t tc_elect_one() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile("{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %2;\n\t@%%px mov.s32 %1, 1;\n\tmov.s32 %0, %%rx;\n\t}"
+                 : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 /* generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads, TMA) */
