@@ -40,6 +40,22 @@ def test_kernels_are_built_for_sm100a(vb):
     assert "sm_100a" in out
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP"):     # tcgen05.mma, TMA tensor load, tcgen05.ld, bulk copy
         assert mnemonic in out, mnemonic
+    # per kernel: the tensor-core attention issues 6 + 6 plane products x 4 k-steps per key block, the persistent GEMM 4 k-steps
+    # per plane and stage (the plane loop is not unrolled); both read their accumulators back with tcgen05.ld
+    per = {}
+    name = None
+    for line in out.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            per[name] = {"UTCHMMA": 0, "UTMALDG": 0, "LDTM": 0}
+        elif name:
+            for m in per[name]:
+                if m in line:
+                    per[name][m] += 1
+    attn = [v for k, v in per.items() if "k_attn_tc" in k]
+    assert attn and attn[0]["UTCHMMA"] == 48 and attn[0]["UTMALDG"] >= 3 and attn[0]["LDTM"] >= 3, attn
+    gemm2 = [v for k, v in per.items() if "k_gemm_tc2" in k]
+    assert len(gemm2) == 5 and all(v["UTCHMMA"] >= 4 and v["UTMALDG"] >= 2 and v["LDTM"] >= 1 for v in gemm2), gemm2
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference headers not on this machine")

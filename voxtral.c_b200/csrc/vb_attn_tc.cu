@@ -8,17 +8,22 @@
  * the split is exact), and a product a*b is evaluated as the six plane products whose weight is >= 2^-18:
  * a0b0, a0b1, a1b0, a1b1, a0b2, a2b0 -- each exact in the f32 accumulator; what is dropped is <= 2^-26 |a||b|, below f32
  * rounding of the sum.  P (the softmax numerators, in [0,1]) is split the same way before P V.  Max / exp / sum are f32 in
- * registers (expf), so the result agrees with the CUDA-core kernels (k_attn_tile64 / k_attn_warp) to f32 rounding.
+ * registers (ex2.approx on (s - m) log2e: relative error 2^-22), so the result agrees with the CUDA-core kernels
+ * (k_attn_tile64 / k_attn_warp) to a few f32 ulps -- below what the tensor core's accumulation order moves.
  *
- * One CTA = 128 queries of one head; keys in blocks of 64.  192 threads:
+ * One CTA = 128 queries of one head; keys in blocks of 64.  320 threads:
  *   warp 0     TMA: Q planes once (3 x [128 x 64] bf16), then per key block K planes (3 x [64 keys x 64 d]) into a 3-slot ring
  *              and V^T planes (3 x [64 d x 64 keys]) into a 2-slot ring, all SWIZZLE_128B boxes
- *   warp 1     one thread issues the MMAs: S(j+1) = Q K(j+1)^T is issued BEFORE P(j) V(j), so the tensor pipe works on the next
- *              scores while the softmax warps turn S(j) into P(j); 24 + 24 tcgen05.mma (M128 N64 K16) per key block
- *   warps 2-5  thread = query row: tcgen05.ld S(j) (64 columns), mask, running max / sum, P(j) -> three bf16 planes written
- *              to shared memory in the SWIZZLE_128B K-major layout the MMA reads, then the deferred O = O*alpha + (P V)(j-1)
- *              from TMEM into 64 registers
+ *   warp 1     MMA issue (whole warp converged, one elected lane issues, vb_tc.cuh:tc_elect_one): S(j+1) = Q K(j+1)^T is issued
+ *              BEFORE P(j) V(j), so the tensor pipe works on the next scores while the softmax warps turn S(j) into P(j);
+ *              24 + 24 tcgen05.mma (M128 N64 K16) per key block
+ *   warps 2-9  softmax, thread = (query row, column half): warps w and w+4 own the same TMEM lane quarter and split the 64
+ *              columns (keys of S, head dims of O).  tcgen05.ld S(j) (32 columns), mask (edge blocks only), running max -- the
+ *              two halves exchange their partial maximum through shared memory + one named barrier -- and sum, P(j) -> three
+ *              bf16 planes written to shared memory in the SWIZZLE_128B K-major layout the MMA reads, then the deferred
+ *              O = O*alpha + (P V)(j-1) from TMEM into 32 registers.  Output: f32 rows, or bf16 planes for the wo GEMM.
  * TMEM: S double-buffered (2 x 64 columns), P V block result double-buffered (2 x 64 columns).
+ * Measured: profiles/r02_encoder.md (188 us per layer at 3196 positions; the CUDA-core kernel k_attn_tile64 took 701 us).
  *
  * V^T: the B operand of P V has to be K-major, i.e. [d][key] with keys contiguous; k_vt_planes transposes V while splitting
  * it.  Q and K planes come from the GEMM's splitter (vb_tc_split_planes).
