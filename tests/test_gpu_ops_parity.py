@@ -178,6 +178,33 @@ def test_causal_attention(vb, ref, seq_q, seq_k, H, Hkv, hd, win, qoff):
     close(a, b, 2e-5)
 
 
+@pytest.mark.parametrize("seq_q,seq_k,win,qoff", [(300, 1500, 750, 1200), (129, 1000, 750, 871), (33, 97, 40, 64)])
+def test_causal_attention_p_in_tensor_memory(vb, ref, seq_q, seq_k, win, qoff):
+    """k_attn_tc_t (VOX_CUDA_ATTN_P=tmem): P stored with tcgen05.st, P V with its A operand in TMEM.  Same plane products in the
+    same order as the shared-memory kernel, so the two must agree to rounding noise; both against the reference."""
+    import os
+    rng = np.random.default_rng(70 + seq_q)
+    H, hd = 32, 64
+    Q = rng.normal(size=(seq_q, H * hd)).astype(np.float32)
+    K = rng.normal(size=(seq_k, H * hd)).astype(np.float32)
+    V = rng.normal(size=(seq_k, H * hd)).astype(np.float32)
+    a, a_t, b = np.empty_like(Q), np.empty_like(Q), np.empty_like(Q)
+    scale = 1.0 / np.sqrt(hd)
+    vb.lib().vox_causal_attention(P(a), P(Q), P(K), P(V), seq_q, seq_k, H, H, hd, scale, win, qoff)
+    old = os.environ.get("VOX_CUDA_ATTN_P")
+    os.environ["VOX_CUDA_ATTN_P"] = "tmem"
+    try:
+        vb.lib().vox_causal_attention(P(a_t), P(Q), P(K), P(V), seq_q, seq_k, H, H, hd, scale, win, qoff)
+    finally:
+        if old is None:
+            del os.environ["VOX_CUDA_ATTN_P"]
+        else:
+            os.environ["VOX_CUDA_ATTN_P"] = old
+    ref.L.vox_causal_attention(P(b), P(Q), P(K), P(V), seq_q, seq_k, H, H, hd, scale, win, qoff)
+    close(a_t, b, 2e-5)
+    close(a_t, a, 1e-6)
+
+
 @pytest.mark.parametrize("hd,heads,pos0", [(128, 8, 0), (64, 32, 180000), (128, 32, 9000)])
 def test_rope(vb, ref, hd, heads, pos0):
     rng = np.random.default_rng(8)
