@@ -11,13 +11,14 @@
  * 24 -- the default, since the third plane costs ~4% of the encoder time and makes the products f32-exact.  All planes accumulate into the SAME TMEM tile, so
  * a split GEMM is simply a K loop that is `nsplit` times longer.
  *
- * Kernel anatomy (one 128 x 128 output tile per CTA, 192 threads):
- *   warp 0    TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 128 rows x 64 bf16) for the A plane
- *             tile and the W tile into a 4-stage shared-memory ring, completion on mbarriers (expect_tx)
- *   warp 1    TMEM allocation + single-thread tcgen05.mma.cta_group::1.kind::f16 issue (M=128, N=128, K=16 x4
- *             per stage), tcgen05.commit releases the stage / publishes the accumulator
- *   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> bias / GELU / residual / SiLU(g)*u
- *             -> global f32
+ * Two kernels, same warp roles (192 threads: warp 0 TMA producer, warp 1 TMEM allocation + MMA issue, warps 2-5 epilogue:
+ * tcgen05.ld 32 lanes x 32 columns -> registers -> epilogue -> global):
+ *   k_gemm_tc   one 128 x 128 output tile per CTA, 4-stage ring of (A plane tile, W tile), planes one after the other
+ *               (round 1; calls with fewer than 512 rows)
+ *   k_gemm_tc2  persistent, 128 x 256 tiles, a stage = W tile + the A tiles of all planes, accumulator double-buffered in
+ *               TMEM, epilogues that write the next kernel's operands (see the comment above it; profiles/r02_encoder.md)
+ * Entry points: vb_gemm_tc (f32 activations: splits, then) -> vb_gemm_tc_planes (pre-split activations); vb_gemm_tc_qkv_rope
+ * (the encoder's wq|wk|wv with bias + RoPE + K/V append + Q/K planes as its epilogue).
  */
 #include "vb_tc.cuh"
 #include <string.h>
