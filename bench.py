@@ -338,10 +338,19 @@ def main():
         ref = g["tokens"]; margin = g["top_val"][:, 0] - g["top_val"][:, 1]
         n_cmp = min(len(ids), len(ref))
         bad = np.nonzero(ids[:n_cmp] != ref[:n_cmp])[0]
+        # a differing id is a near-tie flip if the reference's own top-2 margin there is < 2e-3 (the tests' rule) AND the engine
+        # chose the reference's runner-up; anything else is a parity failure
+        runner_up = g["top_idx"][:, 1]
+        flips = [{"step": int(i), "reference_margin": float(margin[i]), "engine_id_is_reference_runner_up": bool(ids[i] == runner_up[i])}
+                 for i in bad[:16]]
+        near = all(f["reference_margin"] < 2e-3 and f["engine_id_is_reference_runner_up"] for f in flips) and bad.size <= 16
         parity = {"compared_ids": int(n_cmp), "reference_ids": int(len(ref)),
                   "reference": os.path.relpath(gfull, ROOT) + " (unmodified reference on the whole recording, oracle/ref_trace)",
                   "first_mismatch": int(bad[0]) if bad.size else None, "mismatching_ids": int(bad.size),
-                  "reference_margin_at_mismatch": float(margin[bad[0]]) if bad.size else None}
+                  "reference_margin_at_mismatch": float(margin[bad[0]]) if bad.size else None,
+                  "near_tie_flips": flips, "all_mismatches_are_near_ties": bool(near), "ids_equal": bool(bad.size == 0),
+                  "rule": "parity_prefix_ok = every id equals the reference's, except where the reference's own top-2 logit margin is "
+                          "< 2e-3 and the engine chose its runner-up (listed in near_tie_flips)"}
     elif os.path.exists(gpath) and args.seconds >= 60:
         g = np.load(gpath)
         ref = g["tokens"]; margin = g["top_val"][:, 0] - g["top_val"][:, 1]
@@ -353,7 +362,7 @@ def main():
     if rank == 0 and os.environ.get("VOX_BENCH_SAVE_IDS"):   # for an offline comparison with a reference trace made later
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         np.save(os.path.join(ROOT, "gpurun_out", f"bench_ids_{args.seconds:g}s.npy"), np.asarray(ids, dtype=np.int32))
-    parity_ok = bool(parity is not None and parity["first_mismatch"] is None)
+    parity_ok = bool(parity is not None and (parity["first_mismatch"] is None or parity.get("all_mismatches_are_near_ties", False)))
 
     # ---- several streams per weight pass on this GPU (N = 1 only: the scaling run keeps one stream per GPU)
     ms_block = None

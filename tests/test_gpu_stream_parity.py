@@ -88,6 +88,29 @@ def test_two_long_feeds_match_oneshot_reference(engine):
     check_against(g, ids, text)
 
 
+def test_10min_oneshot_matches_reference(engine):
+    """The benchmark's own workload (BASELINE configs[2]: 10 minutes, one feed -- one encoder call over 30196 positions, 7511
+    decoder steps up to KV length 7549) against the unmodified reference's trace of the same recording (~3 h of host time to make,
+    tools/make_goldens.py ... slim).  bench.py compares the same ids in every run (`parity_prefix`)."""
+    g = golden("synth_s600_oneshot")
+    pcm = read_wav_f32(synth_wav(600))
+    assert pcm.size == int(g["samples"])
+    ids, text, counts = run_stream(engine, pcm)
+    assert counts["mel_frames"] == 60392 and counts["adapter_tokens"] == 7549
+    ref_ids, margin, runner_up = g["tokens"], g["top_val"][:, 0] - g["top_val"][:, 1], g["top_idx"][:, 1]
+    assert len(ids) == len(ref_ids) == 7511
+    bad = np.nonzero(ids != ref_ids)[0]
+    # Unlike check_against this does not stop at the first near-tie: on this checkpoint the decoder re-converges after a flipped id,
+    # so every later step stays comparable.  A differing id must be the reference's runner-up at a step where the reference's own
+    # top-2 margin is below 2e-3 (the near-tie rule of this file), and there may be only a handful of them.
+    for i in bad:
+        print(f"near-tie at step {i}: reference {ref_ids[i]} (margin {margin[i]:.3e}), engine {ids[i]}")
+        assert margin[i] < 2e-3 and ids[i] == runner_up[i], f"token mismatch at step {i}: {ids[i]} vs {ref_ids[i]} (reference margin {margin[i]:.3e})"
+    assert bad.size <= 4, f"{bad.size} near-tie flips in 7511 steps"
+    if bad.size == 0:
+        assert text == g["text"].tobytes()
+
+
 def test_chunking_invariance(engine):
     """The incremental path must not depend on how the caller slices the audio (same mel frames, same
     conv/encoder rows up to f32 reordering) -- the tiny-interval run exercises the conv tails, the odd

@@ -8,6 +8,13 @@
  *                             RMSNorm -> SwiGLU(w1,w3) -> w2(+bias)+res ; final RMSNorm.
  *   vb_adapter_dev         == vox_adapter_forward (voxtral_encoder.c:642-674)
  *
+ * Two routes through a layer, same arithmetic per element (bit-identical, tests/test_gpu_blocks_parity.py):
+ *   calls of >= 512 positions  every producer writes the next tensor-core kernel's operands as bf16 planes: RMSNorm -> planes ->
+ *                              wq|wk|wv GEMM whose epilogue adds the bias, applies RoPE, appends K/V to the cache and writes the
+ *                              attention's Q/K planes -> tcgen05 attention -> planes -> wo -> RMSNorm -> planes -> w1|w3 with
+ *                              SiLU(g)*u -> planes -> w2 (vb_gemm_tc.cu, vb_attn_tc.cu)
+ *   shorter calls              one kernel per step with f32 rows in between (vb_ops.cu), the GEMMs splitting their input themselves
+ *
  * Encoder KV: the reference keeps a growing f32 cache that it compacts to the last 750
  * positions before every call (voxtral_encoder.c:388-406,463-466).  Only those 750 rows can
  * ever be attended again.  HBM holds a [32][750 + 2048][2048] cache per K and V:
