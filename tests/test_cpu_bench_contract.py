@@ -43,3 +43,18 @@ def test_command_line_contract():
                 '"vs_baseline"', '"dtype"', '"data"', '"config"', '"e2e"', '"gpu_launches"', '"clocks"', '"roofline"', '"cpu_baseline"',
                 '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"traffic"', '"frac"', '"peak"', '"achieved"', '"bound"'):
         assert key in src, key
+
+
+def test_recorded_10min_ids_against_the_reference_trace():
+    """The ids recorded on a B200 for the benchmark's 10-minute workload (profiles/r02_ids_600s_*.npy, saved by bench.py with
+    VOX_BENCH_SAVE_IDS=1 and tools/dump_ids.py) against the reference's own trace of that recording: the claim of
+    profiles/r02_bench.md, checkable without a GPU."""
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "synth_s600_oneshot.npz"))
+    ref, margin, runner_up = g["tokens"], g["top_val"][:, 0] - g["top_val"][:, 1], g["top_idx"][:, 1]
+    assert len(ref) == 7511
+    exact = np.load(os.path.join(ROOT, "profiles", "r02_ids_600s_gemm_v1.npy"))
+    assert np.array_equal(exact, ref)                                     # plane-major GEMM everywhere: id for id
+    ids = np.load(os.path.join(ROOT, "profiles", "r02_ids_600s_default.npy"))
+    bad = np.nonzero(ids != ref)[0]
+    assert bad.tolist() == [1864] and margin[1864] < 3e-5 and ids[1864] == runner_up[1864]
