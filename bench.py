@@ -350,7 +350,9 @@ def main():
                   "reference_margin_at_mismatch": float(margin[bad[0]]) if bad.size else None,
                   "near_tie_flips": flips, "all_mismatches_are_near_ties": bool(near), "ids_equal": bool(bad.size == 0),
                   "rule": "parity_prefix_ok = every id equals the reference's, except where the reference's own top-2 logit margin is "
-                          "< 2e-3 and the engine chose its runner-up (listed in near_tie_flips)"}
+                          "< 2e-3 and the engine chose its runner-up (listed in near_tie_flips)",
+                  "note": "recorded on a B200 (profiles/r02_bench.md): with VOX_CUDA_GEMM=v1 (plane-major accumulation in every tcgen05 "
+                          "GEMM, 0.6 x the encoder throughput) the same build reproduces all 7511 ids of this recording"}
     elif os.path.exists(gpath) and args.seconds >= 60:
         g = np.load(gpath)
         ref = g["tokens"]; margin = g["top_val"][:, 0] - g["top_val"][:, 1]
